@@ -1,0 +1,95 @@
+// C-ABI dispatch layer of libicf_b200: validation, error reporting, kernel-family selection.
+#include "icf_common.cuh"
+
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+
+int icf_simt_conv_forward(const icf_conv_args* a, cudaStream_t st);
+int icf_simt_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st);
+
+namespace icf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return 2;
+  }
+  return 0;
+}
+
+static std::atomic<int> g_tc{-1};
+
+}  // namespace icf
+
+extern "C" {
+
+const char* icf_last_error(void) { return icf::g_err; }
+int icf_version(void) { return ICF_VERSION; }
+
+int icf_tc_enabled(void) {
+  int v = icf::g_tc.load();
+  if (v < 0) {
+    const char* e = getenv("ICF_DISABLE_TC");
+    v = (e && e[0] && e[0] != '0') ? 0 : 1;
+    icf::g_tc.store(v);
+  }
+  return v;
+}
+void icf_set_tc_enabled(int on) { icf::g_tc.store(on ? 1 : 0); }
+
+static int validate_conv(const icf_conv_args* a) {
+  ICF_REQUIRE(a, "icf_conv_forward: null args");
+  ICF_REQUIRE(a->dtype == ICF_F32 || a->dtype == ICF_BF16, "icf_conv_forward: dtype %d", a->dtype);
+  ICF_REQUIRE(a->form == ICF_FORM_GATHER || a->form == ICF_FORM_TRANSPOSED, "icf_conv_forward: form %d",
+              a->form);
+  ICF_REQUIRE(a->src && a->w && a->dst, "icf_conv_forward: null tensor pointer");
+  ICF_REQUIRE(a->N >= 0 && a->H > 0 && a->W > 0 && a->C > 0 && a->P > 0 && a->Q > 0 && a->K > 0 && a->R > 0 &&
+                  a->S > 0 && a->stride > 0 && a->pad >= 0,
+              "icf_conv_forward: non-positive extent");
+  ICF_REQUIRE(a->in_pitch >= a->C && a->out_pitch >= a->K && a->w_rows >= a->K && a->w_pitch >= a->C,
+              "icf_conv_forward: pitch/rows smaller than channel count (C=%d pitch=%d, K=%d pitch=%d rows=%d)",
+              a->C, a->in_pitch, a->K, a->out_pitch, a->w_rows);
+  ICF_REQUIRE(!a->accumulate || a->out_f32 || a->dtype == ICF_F32, "icf_conv_forward: accumulate needs f32 dst");
+  return 0;
+}
+
+int icf_conv_forward(const icf_conv_args* a, void* stream) {
+  if (int r = validate_conv(a)) return r;
+  if (a->N == 0) return 0;
+  cudaStream_t st = icf::as_stream(stream);
+  if (a->dtype == ICF_BF16 && icf_tc_enabled()) {
+    int r = icf_tc_conv_forward(a, st);
+    if (r >= 0) return r;
+  }
+  return icf_simt_conv_forward(a, st);
+}
+
+int icf_conv_wgrad(const icf_wgrad_args* a, void* stream) {
+  ICF_REQUIRE(a, "icf_conv_wgrad: null args");
+  ICF_REQUIRE(a->dtype == ICF_F32 || a->dtype == ICF_BF16, "icf_conv_wgrad: dtype %d", a->dtype);
+  ICF_REQUIRE(a->small_t && a->big_t && a->dw, "icf_conv_wgrad: null tensor pointer");
+  ICF_REQUIRE(a->N >= 0 && a->P > 0 && a->Q > 0 && a->A > 0 && a->H > 0 && a->W > 0 && a->B > 0 && a->R > 0 &&
+                  a->S > 0 && a->stride > 0 && a->pad >= 0 && a->a_pitch >= a->A && a->b_pitch >= a->B,
+              "icf_conv_wgrad: bad extents");
+  if (a->N == 0) return 0;
+  cudaStream_t st = icf::as_stream(stream);
+  if (a->dtype == ICF_BF16 && icf_tc_enabled()) {
+    int r = icf_tc_conv_wgrad(a, st);
+    if (r >= 0) return r;
+  }
+  return icf_simt_conv_wgrad(a, st);
+}
+
+}  // extern "C"

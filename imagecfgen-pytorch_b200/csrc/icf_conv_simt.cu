@@ -1,0 +1,247 @@
+// SIMT implicit-GEMM convolution kernels: the fp32 path (1e-3 parity mode) and the fallback for shapes the
+// tcgen05 path does not take (odd channel counts such as the K=1 logits layer).
+//
+// forward / dgrad : dst[m][k] = epi( sum_{tap,c} src[pix(m,tap)][c] * w[k][tap][c] ),  m = (n,p,q)
+// wgrad           : dw[a][tap][b] += sum_m small[m][a] * big[pix(m,tap)][b]
+#include "icf_common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 8, NT = 256;
+
+template <typename T, int FORM, typename TO>
+__global__ void __launch_bounds__(NT) conv_simt_kernel(const icf_conv_args a) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  __shared__ float Ss[2][BN];
+  const int tid = threadIdx.x;
+  const int PQ = a.P * a.Q;
+  const int64_t M = (int64_t)a.N * PQ;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int taps = a.R * a.S;
+
+  // loader role: one (row, channel-pair) per thread for both operand tiles
+  const int lrow = tid >> 2, lc = (tid & 3) * 2;
+  const int64_t lm = m0 + lrow;
+  const bool lvalid = lm < M;
+  int ln = 0, lp = 0, lq = 0;
+  if (lvalid) {
+    ln = (int)(lm / PQ);
+    int rem = (int)(lm - (int64_t)ln * PQ);
+    lp = rem / a.Q;
+    lq = rem - lp * a.Q;
+  }
+  const int wrow = n0 + lrow;
+  const bool bvalid = wrow < a.w_rows;
+  const T* __restrict__ src = reinterpret_cast<const T*>(a.src);
+  const T* __restrict__ w = reinterpret_cast<const T*>(a.w);
+
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int tap = 0; tap < taps; ++tap) {
+    const int r = tap / a.S, s = tap - r * a.S;
+    int iy, ix;
+    bool v = lvalid;
+    if (FORM == ICF_FORM_GATHER) {
+      iy = lp * a.stride - a.pad + r;
+      ix = lq * a.stride - a.pad + s;
+      v = v && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+    } else {
+      const int uy = lp + a.pad - r, ux = lq + a.pad - s;
+      v = v && uy >= 0 && ux >= 0 && (uy % a.stride) == 0 && (ux % a.stride) == 0;
+      iy = uy / a.stride;
+      ix = ux / a.stride;
+      v = v && iy < a.H && ix < a.W;
+    }
+    if (!__syncthreads_or(v)) continue;   // no pixel of this tile touches the tap (padding / parity)
+    const T* ap = src + ((int64_t)(ln * a.H + iy) * a.W + ix) * a.in_pitch;
+    const T* bp = w + ((int64_t)wrow * taps + tap) * a.w_pitch;
+    for (int c0 = 0; c0 < a.C; c0 += BK) {
+      const int c = c0 + lc;
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+      if (v) {
+        if (c < a.C) a0 = icf::ldf(ap + c);
+        if (c + 1 < a.C) a1 = icf::ldf(ap + c + 1);
+      }
+      if (bvalid) {
+        if (c < a.C) b0 = icf::ldf(bp + c);
+        if (c + 1 < a.C) b1 = icf::ldf(bp + c + 1);
+      }
+      As[lc][lrow] = a0;
+      As[lc + 1][lrow] = a1;
+      Bs[lc][lrow] = b0;
+      Bs[lc + 1][lrow] = b1;
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        const float aa[4] = {av.x, av.y, av.z, av.w};
+        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue: bias + activation + Dropout2d mask (+ BatchNorm partial sums) -------------------
+  TO* __restrict__ dst = reinterpret_cast<TO*>(a.dst);
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int n = (int)(m / PQ);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = n0 + tx * 4 + j;
+      if (k >= a.K) continue;
+      float val = acc[i][j] + (a.bias ? a.bias[k] : 0.f);
+      val = icf::apply_act(val, a.act, a.slope);
+      if (a.out_mask) val *= a.out_mask[(int64_t)n * a.mask_pitch + k];
+      TO* o = dst + m * a.out_pitch + k;
+      if (a.accumulate) val += icf::ldf(o);
+      icf::stf(o, val);
+      const float stored = icf::ldf(o);   // statistics of what the consumer will read
+      s1[j] += stored;
+      s2[j] += stored * stored;
+    }
+  }
+  if (a.stats) {
+    if (tid < BN) { Ss[0][tid] = 0.f; Ss[1][tid] = 0.f; }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&Ss[0][tx * 4 + j], s1[j]);
+      atomicAdd(&Ss[1][tx * 4 + j], s2[j]);
+    }
+    __syncthreads();
+    if (tid < BN && n0 + tid < a.K) {
+      atomicAdd(a.stats + n0 + tid, Ss[0][tid]);
+      atomicAdd(a.stats + a.K + n0 + tid, Ss[1][tid]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT) wgrad_simt_kernel(const icf_wgrad_args a, int splits,
+                                                        int64_t pix_per_split) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int taps = a.R * a.S;
+  const int tap = blockIdx.z % taps;
+  const int split = blockIdx.z / taps;
+  const int r = tap / a.S, s = tap - r * a.S;
+  const int PQ = a.P * a.Q;
+  const int64_t M = (int64_t)a.N * PQ;
+  const int64_t mb = (int64_t)split * pix_per_split;
+  const int64_t me = min(M, mb + pix_per_split);
+  const int a0 = blockIdx.x * BM, b0 = blockIdx.y * BN;
+  const T* __restrict__ sm = reinterpret_cast<const T*>(a.small_t);
+  const T* __restrict__ bg = reinterpret_cast<const T*>(a.big_t);
+
+  const int lpix = tid >> 5;           // 0..7
+  const int lch = (tid & 31) * 2;      // 0..62
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int64_t mc = mb; mc < me; mc += BK) {
+    const int64_t m = mc + lpix;
+    float x0 = 0.f, x1 = 0.f, y0 = 0.f, y1 = 0.f;
+    if (m < me) {
+      const int n = (int)(m / PQ);
+      const int rem = (int)(m - (int64_t)n * PQ);
+      const int p = rem / a.Q, q = rem - p * a.Q;
+      const T* sp = sm + m * a.a_pitch;
+      if (a0 + lch < a.A) x0 = icf::ldf(sp + a0 + lch);
+      if (a0 + lch + 1 < a.A) x1 = icf::ldf(sp + a0 + lch + 1);
+      const int iy = p * a.stride - a.pad + r, ix = q * a.stride - a.pad + s;
+      if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
+        const T* bp = bg + ((int64_t)(n * a.H + iy) * a.W + ix) * a.b_pitch;
+        if (b0 + lch < a.B) y0 = icf::ldf(bp + b0 + lch);
+        if (b0 + lch + 1 < a.B) y1 = icf::ldf(bp + b0 + lch + 1);
+      }
+    }
+    As[lpix][lch] = x0;
+    As[lpix][lch + 1] = x1;
+    Bs[lpix][lch] = y0;
+    Bs[lpix][lch + 1] = y1;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w};
+      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ai = a0 + ty * 4 + i;
+    if (ai >= a.A) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int bj = b0 + tx * 4 + j;
+      if (bj >= a.B) continue;
+      atomicAdd(a.dw + ((int64_t)ai * taps + tap) * a.B + bj, acc[i][j]);
+    }
+  }
+}
+
+template <typename T, int FORM>
+int launch_conv(const icf_conv_args* a, cudaStream_t st) {
+  const int64_t M = (int64_t)a->N * a->P * a->Q;
+  dim3 grid(icf::cdiv(M, BM), icf::cdiv(a->K, BN));
+  const bool out_f32 = a->out_f32 || a->dtype == ICF_F32;
+  if (out_f32) conv_simt_kernel<T, FORM, float><<<grid, NT, 0, st>>>(*a);
+  else conv_simt_kernel<T, FORM, T><<<grid, NT, 0, st>>>(*a);
+  return icf::check_launch("conv_simt");
+}
+
+}  // namespace
+
+int icf_simt_conv_forward(const icf_conv_args* a, cudaStream_t st) {
+  if (a->dtype == ICF_F32) {
+    return a->form == ICF_FORM_GATHER ? launch_conv<float, ICF_FORM_GATHER>(a, st)
+                                      : launch_conv<float, ICF_FORM_TRANSPOSED>(a, st);
+  }
+  return a->form == ICF_FORM_GATHER ? launch_conv<__nv_bfloat16, ICF_FORM_GATHER>(a, st)
+                                    : launch_conv<__nv_bfloat16, ICF_FORM_TRANSPOSED>(a, st);
+}
+
+int icf_simt_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
+  const int taps = a->R * a->S;
+  const int64_t M = (int64_t)a->N * a->P * a->Q;
+  const int gx = icf::cdiv(a->A, BM), gy = icf::cdiv(a->B, BN);
+  // enough splits over the pixel dimension to fill the 148 SMs a few times
+  int64_t want = (148 * 4 + (int64_t)gx * gy * taps - 1) / ((int64_t)gx * gy * taps);
+  int64_t max_splits = (M + 255) / 256;
+  int splits = (int)(want < 1 ? 1 : (want > max_splits ? max_splits : want));
+  if (splits < 1) splits = 1;
+  if ((int64_t)taps * splits > 65535) splits = 65535 / taps;
+  int64_t pps = (M + splits - 1) / splits;
+  pps = (pps + BK - 1) / BK * BK;
+  dim3 grid(gx, gy, taps * splits);
+  if (a->dtype == ICF_F32) wgrad_simt_kernel<float><<<grid, NT, 0, st>>>(*a, splits, pps);
+  else wgrad_simt_kernel<__nv_bfloat16><<<grid, NT, 0, st>>>(*a, splits, pps);
+  return icf::check_launch("wgrad_simt");
+}

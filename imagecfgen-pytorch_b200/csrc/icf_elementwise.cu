@@ -1,0 +1,588 @@
+// HBM-bound kernels of the BiGAN hot path: attribute/latent feature assembly, BatchNorm pieces, the fused
+// activation/dropout/BN backward, BCE-with-logits, Adam, weight (un)packing.
+#include "icf_common.cuh"
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------
+// argmax over rows (first maximum wins, torch.argmax semantics; all-zero row -> 0)
+// ------------------------------------------------------------------------------------------------
+__global__ void argmax_rows_kernel(const void* x, int dt, int n, int k, int32_t* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int best = 0;
+  if (dt == 2) {
+    const int32_t* p = reinterpret_cast<const int32_t*>(x) + (int64_t)i * k;
+    int32_t bv = p[0];
+    for (int j = 1; j < k; ++j) if (p[j] > bv) { bv = p[j]; best = j; }
+  } else if (dt == 3) {
+    const int64_t* p = reinterpret_cast<const int64_t*>(x) + (int64_t)i * k;
+    int64_t bv = p[0];
+    for (int j = 1; j < k; ++j) if (p[j] > bv) { bv = p[j]; best = j; }
+  } else {
+    float bv = icf::ld_any(x, dt, (int64_t)i * k);
+    for (int j = 1; j < k; ++j) {
+      float v = icf::ld_any(x, dt, (int64_t)i * k + j);
+      if (v > bv) { bv = v; best = j; }
+    }
+  }
+  out[i] = best;
+}
+
+// ------------------------------------------------------------------------------------------------
+// image feature stack: [x | tanh(upsample16(emb[idx])) ... | const planes ...] * mask, NHWC pitch 8
+// one thread per pixel writes the whole (<= 8 channel) vector
+// ------------------------------------------------------------------------------------------------
+__global__ void imgfeat_fwd_kernel(const icf_imgfeat_args a) {
+  const int64_t total = (int64_t)a.N * a.H * a.W;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int hw = a.H * a.W;
+  const int n = (int)(i / hw);
+  const int rem = (int)(i - (int64_t)n * hw);
+  const int y = rem / a.W, x = rem - y * a.W;
+  const int cy = min((y * 16) / a.H, 15), cx = min((x * 16) / a.W, 15);   // nearest: floor(dst*16/size)
+  const float* mk = a.mask ? a.mask + (int64_t)n * a.mask_pitch : nullptr;
+  int ch = 0;
+  float v = icf::ld_any(a.x, a.x_dtype, i * a.x_pitch);
+  icf::st_any(a.feat, a.dtype, i * a.feat_pitch + ch, mk ? v * mk[ch] : v);
+  ++ch;
+  for (int e = 0; e < a.n_emb; ++e, ++ch) {
+    const float t = tanhf(a.emb_table[e][(int64_t)a.emb_index[e][n] * 256 + cy * 16 + cx]);
+    icf::st_any(a.feat, a.dtype, i * a.feat_pitch + ch, mk ? t * mk[ch] : t);
+  }
+  for (int e = 0; e < a.n_cont; ++e, ++ch) {
+    const float t = a.cont[e][n];
+    icf::st_any(a.feat, a.dtype, i * a.feat_pitch + ch, mk ? t * mk[ch] : t);
+  }
+  for (; ch < a.feat_pitch; ++ch) icf::st_any(a.feat, a.dtype, i * a.feat_pitch + ch, 0.f);
+}
+
+// gradient into the embedding tables: one warp per (sample, plane, cell): reduce the cell's pixel block
+__global__ void imgfeat_bwd_kernel(const icf_imgfeat_args a) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t total = (int64_t)a.N * a.n_emb * 256;
+  if (warp >= total) return;
+  const int cell = (int)(warp & 255);
+  const int e = (int)((warp >> 8) % a.n_emb);
+  const int n = (int)((warp >> 8) / a.n_emb);
+  const int cy = cell >> 4, cx = cell & 15;
+  // destination rows y with floor(y*16/H) == cy  <=>  y in [ceil(cy*H/16), ceil((cy+1)*H/16))
+  const int y0 = (cy * a.H + 15) / 16, y1 = ((cy + 1) * a.H + 15) / 16;
+  const int x0 = (cx * a.W + 15) / 16, x1 = ((cx + 1) * a.W + 15) / 16;
+  const int bw = x1 - x0, cnt = (y1 - y0) * bw;
+  const int ch = 1 + e;
+  float sum = 0.f;
+  for (int t = lane; t < cnt; t += 32) {
+    const int y = y0 + t / bw, x = x0 + t % bw;
+    sum += icf::ld_any(a.dfeat, a.dtype, (((int64_t)n * a.H + y) * a.W + x) * a.feat_pitch + ch);
+  }
+  sum = icf::warp_sum(sum);
+  if (lane == 0) {
+    const int idx = a.emb_index[e][n];
+    const float t = tanhf(a.emb_table[e][(int64_t)idx * 256 + cell]);
+    float g = sum * (1.f - t * t);
+    if (a.mask) g *= a.mask[(int64_t)n * a.mask_pitch + ch];
+    if (g != 0.f) atomicAdd(a.demb_table[e] + (int64_t)idx * 256 + cell, g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// latent feature vector: [z | onehot_i @ table_i ... | cont ... | 0 pad]
+// ------------------------------------------------------------------------------------------------
+__global__ void latfeat_fwd_kernel(const icf_latfeat_args a) {
+  const int64_t total = (int64_t)a.N * a.feat_pitch;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = (int)(i / a.feat_pitch);
+  const int j = (int)(i - (int64_t)n * a.feat_pitch);
+  float v = 0.f;
+  if (j < a.latent) {
+    v = icf::ld_any(a.z, a.z_dtype, (int64_t)n * a.z_pitch + j);
+  } else {
+    const int jj = j - a.latent;
+    const int e = jj >> 8;
+    if (e < a.n_emb) {
+      const int col = jj & 255;
+      const int K = a.emb_k[e];
+      const float* oh = a.onehot[e] + (int64_t)n * K;
+      const float* tb = a.emb_table[e];
+      for (int k = 0; k < K; ++k) v = fmaf(oh[k], tb[k * 256 + col], v);
+    } else {
+      const int ci = jj - a.n_emb * 256;
+      if (ci < a.n_cont) v = a.cont[ci][n];
+    }
+  }
+  icf::st_any(a.feat, a.dtype, i, v);
+}
+
+// dz, d_onehot, d_cont: one thread per element of the un-padded feature row
+__global__ void latfeat_bwd_rows_kernel(const icf_latfeat_args a) {
+  const int width = a.latent + a.n_cont;
+  int tot_k = 0;
+  for (int e = 0; e < a.n_emb; ++e) tot_k += a.emb_k[e];
+  const int per_row = width + tot_k;
+  const int64_t total = (int64_t)a.N * per_row;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = (int)(i / per_row);
+  int j = (int)(i - (int64_t)n * per_row);
+  const int64_t row = (int64_t)n * a.feat_pitch;
+  if (j < a.latent) {
+    if (a.dz) a.dz[(int64_t)n * a.latent + j] = icf::ld_any(a.dfeat, a.dtype, row + j);
+    return;
+  }
+  j -= a.latent;
+  if (j < a.n_cont) {
+    if (a.dcont[j]) a.dcont[j][n] = icf::ld_any(a.dfeat, a.dtype, row + a.latent + a.n_emb * 256 + j);
+    return;
+  }
+  j -= a.n_cont;
+  for (int e = 0; e < a.n_emb; ++e) {
+    if (j < a.emb_k[e]) {
+      if (a.donehot[e]) {
+        const float* tb = a.emb_table[e] + (int64_t)j * 256;
+        float s = 0.f;
+        for (int col = 0; col < 256; ++col)
+          s = fmaf(icf::ld_any(a.dfeat, a.dtype, row + a.latent + e * 256 + col), tb[col], s);
+        a.donehot[e][(int64_t)n * a.emb_k[e] + j] = s;
+      }
+      return;
+    }
+    j -= a.emb_k[e];
+  }
+}
+
+// d_table[e][k][col] += sum_n onehot[n][k] * dfeat[n][latent + e*256 + col]; block per (e,k), thread per col
+__global__ void latfeat_bwd_table_kernel(const icf_latfeat_args a, int e) {
+  const int k = blockIdx.x;
+  const int col = threadIdx.x;   // 256 threads
+  const int K = a.emb_k[e];
+  float s = 0.f;
+  for (int n = 0; n < a.N; ++n) {
+    const float oh = a.onehot[e][(int64_t)n * K + k];
+    if (oh != 0.f)
+      s = fmaf(oh, icf::ld_any(a.dfeat, a.dtype, (int64_t)n * a.feat_pitch + a.latent + e * 256 + col), s);
+  }
+  a.demb_table[e][(int64_t)k * 256 + col] += s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm finalize: stats -> scale/shift (+ running stats), then clear stats for the next forward
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(float* stats, int C, double count, const float* gamma, const float* beta,
+                                   float eps, float momentum, float* rmean, float* rvar, int64_t* nbt,
+                                   float* scale, float* shift, float* save_mean, float* save_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  const double mean = (double)stats[c] / count;
+  double var = (double)stats[C + c] / count - mean * mean;   // biased variance normalises
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale[c] = g * invstd;
+  shift[c] = b - (float)mean * g * invstd;
+  if (save_mean) save_mean[c] = (float)mean;
+  if (save_invstd) save_invstd[c] = invstd;
+  if (rmean) rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mean;
+  if (rvar) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+  }
+  stats[c] = 0.f;
+  stats[C + c] = 0.f;
+}
+
+// u = mask[n,c] * (scale[c]*y + shift[c])   (any of scale/shift/mask may be NULL), with dtype conversion
+__global__ void scale_shift_mask_kernel(const void* y, int ydt, int ypitch, void* u, int udt, int upitch,
+                                        int64_t pixels, int pps, int C, const float* scale,
+                                        const float* shift, const float* mask, int mpitch) {
+  const int64_t total = pixels * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / C;
+    const int c = (int)(i - pix * C);
+    float v = icf::ld_any(y, ydt, pix * ypitch + c);
+    if (scale) v = fmaf(v, scale[c], shift ? shift[c] : 0.f);
+    if (mask) v *= mask[(pix / pps) * mpitch + c];
+    icf::st_any(u, udt, pix * upitch + c, v);
+  }
+}
+
+// per-channel sums of du and du*xhat over all pixels; grid (channel groups of 32, pixel slabs)
+__global__ void bn_bwd_reduce_kernel(const void* dU, int ddt, int dpitch, const void* y, int ydt, int ypitch,
+                                     int64_t pixels, int pps, int C, const float* mask, int mpitch,
+                                     const float* mean, const float* invstd, float* sums) {
+  __shared__ float red[2][8][33];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;     // 32 channels x 8 pixel lanes
+  const int c = blockIdx.x * 32 + cx;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    const float mu = mean[c], is = invstd[c];
+    for (int64_t pix = (int64_t)blockIdx.y * 8 + py; pix < pixels; pix += (int64_t)gridDim.y * 8) {
+      float g = icf::ld_any(dU, ddt, pix * dpitch + c);
+      if (mask) g *= mask[(pix / pps) * mpitch + c];
+      const float xh = (icf::ld_any(y, ydt, pix * ypitch + c) - mu) * is;
+      s0 += g;
+      s1 = fmaf(g, xh, s1);
+    }
+  }
+  red[0][py][cx] = s0;
+  red[1][py][cx] = s1;
+  __syncthreads();
+  if (py == 0 && c < C) {
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { t0 += red[0][k][cx]; t1 += red[1][k][cx]; }
+    atomicAdd(sums + c, t0);
+    atomicAdd(sums + C + c, t1);
+  }
+}
+
+// fused backward of [bias -> act -> dropout] (+ BatchNorm(+dropout) that consumed the output)
+__global__ void act_backward_kernel(const icf_actbwd_args a) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float sb = 0.f;
+  if (c < a.C) {
+    float g_scale = 1.f, m0 = 0.f, m1 = 0.f, mu = 0.f, is = 0.f;
+    const bool bn = a.bn_sums != nullptr;
+    if (bn) {
+      const float invM = 1.f / (float)a.pixels;
+      mu = a.bn_mean[c];
+      is = a.bn_invstd[c];
+      g_scale = a.bn_gamma[c] * is;
+      m0 = a.bn_sums[c] * invM;
+      m1 = a.bn_sums[a.C + c] * invM;
+      if (blockIdx.y == 0 && py == 0) {
+        if (a.bn_dgamma) a.bn_dgamma[c] += a.bn_sums[a.C + c];
+        if (a.bn_dbeta) a.bn_dbeta[c] += a.bn_sums[c];
+      }
+    }
+    for (int64_t pix = (int64_t)blockIdx.y * 8 + py; pix < a.pixels; pix += (int64_t)gridDim.y * 8) {
+      const int64_t n = pix / a.pixels_per_sample;
+      float g = icf::ld_any(a.dOut, a.d_dtype, pix * a.d_pitch + c);
+      const float yv = icf::ld_any(a.y, a.y_dtype, pix * a.y_pitch + c);
+      if (bn) {
+        if (a.bn_mask) g *= a.bn_mask[n * a.bn_mask_pitch + c];
+        const float xh = (yv - mu) * is;
+        g = g_scale * (g - m0 - xh * m1);
+      }
+      if (a.out_mask) g *= a.out_mask[n * a.mask_pitch + c];
+      g *= icf::act_grad_from_output(yv, a.act, a.slope);
+      icf::st_any(a.dPre, a.p_dtype, pix * a.p_pitch + c, g);
+      sb += g;
+    }
+  }
+  if (a.dbias) {
+    red[py][cx] = sb;
+    __syncthreads();
+    if (py == 0 && c < a.C) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][cx];
+      atomicAdd(a.dbias + (a.bias_mod > 0 ? c % a.bias_mod : c), t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BCE with logits (mean) forward+backward; sigmoid mean (phase-D scores). Single block.
+// ------------------------------------------------------------------------------------------------
+__global__ void bce_logits_kernel(const void* logits, int ldt, int lpitch, int n, float target, float weight,
+                                  float* loss_out, void* dl, int ddt, int dpitch) {
+  __shared__ float red[32];
+  float s = 0.f;
+  const float invn = 1.f / (float)n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float l = icf::ld_any(logits, ldt, (int64_t)i * lpitch);
+    s += fmaxf(l, 0.f) - l * target + log1pf(expf(-fabsf(l)));
+    if (dl) {
+      const float sig = 1.f / (1.f + expf(-l));
+      icf::st_any(dl, ddt, (int64_t)i * dpitch, weight * (sig - target) * invn);
+    }
+  }
+  s = icf::block_sum(s, red);
+  if (threadIdx.x == 0 && loss_out) atomicAdd(loss_out, weight * s * invn);
+}
+
+__global__ void sigmoid_mean_kernel(const void* logits, int ldt, int lpitch, int n, float* out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    s += 1.f / (1.f + expf(-icf::ld_any(logits, ldt, (int64_t)i * lpitch)));
+  s = icf::block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out, s / (float)n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam over a flat buffer. state = {step, lr, beta1, beta2, eps, grad_scale}; the tick kernel advances
+// the step so that a captured graph replays correctly.
+// ------------------------------------------------------------------------------------------------
+__global__ void adam_tick_kernel(float* state) { state[0] += 1.f; }
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, const float* __restrict__ state) {
+  const float step = state[0], lr = state[1], b1 = state[2], b2 = state[3], eps = state[4], gs = state[5];
+  const float bc1 = 1.f - powf(b1, step);
+  const float bc2s = sqrtf(1.f - powf(b2, step));
+  const float step_size = lr / bc1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      float4 pv = *reinterpret_cast<float4*>(p + i);
+      const float4 gv = *reinterpret_cast<const float4*>(g + i);
+      float4 mv = *reinterpret_cast<float4*>(m + i);
+      float4 vv = *reinterpret_cast<float4*>(v + i);
+      float* pp = &pv.x; const float* gg = &gv.x; float* mm = &mv.x; float* vvp = &vv.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gr = gg[k] * gs;
+        mm[k] = b1 * mm[k] + (1.f - b1) * gr;
+        vvp[k] = b2 * vvp[k] + (1.f - b2) * gr * gr;
+        pp[k] -= step_size * mm[k] / (sqrtf(vvp[k]) / bc2s + eps);
+      }
+      *reinterpret_cast<float4*>(p + i) = pv;
+      *reinterpret_cast<float4*>(m + i) = mv;
+      *reinterpret_cast<float4*>(v + i) = vv;
+    } else {
+      for (int64_t k = i; k < n; ++k) {
+        const float gr = g[k] * gs;
+        m[k] = b1 * m[k] + (1.f - b1) * gr;
+        v[k] = b2 * v[k] + (1.f - b2) * gr * gr;
+        p[k] -= step_size * m[k] / (sqrtf(v[k]) / bc2s + eps);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight pack / gradient unpack (3-index permutation, see icf.h)
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_kernel(const float* __restrict__ src, void* dst, int ddt, const icf_perm p) {
+  const int64_t total = p.d0_pad * p.d1 * p.d2_pad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i2 = i % p.d2_pad;
+    const int64_t t = i / p.d2_pad;
+    const int64_t i1 = t % p.d1, i0 = t / p.d1;
+    float v = 0.f;
+    if (i2 < p.d2 && i0 < p.d0) v = src[i0 * p.s0 + i1 * p.s1 + i2 * p.s2];
+    icf::st_any(dst, ddt, i, v);
+  }
+}
+
+__global__ void unpack_kernel(const float* __restrict__ src, float* dst, const icf_perm p, int atomic_add) {
+  const int64_t total = p.d0 * p.d1 * p.d2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i2 = i % p.d2;
+    const int64_t t = i / p.d2;
+    const int64_t i1 = t % p.d1, i0 = t / p.d1;
+    const float v = src[(i0 * p.d1 + i1) * p.d2_pad + i2];
+    float* o = dst + i0 * p.s0 + i1 * p.s1 + i2 * p.s2;
+    if (atomic_add) atomicAdd(o, v);
+    else *o = v;
+  }
+}
+
+__global__ void cast_kernel(const void* src, int sdt, void* dst, int ddt, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    icf::st_any(dst, ddt, i, icf::ld_any(src, sdt, i));
+}
+
+__global__ void fill_kernel(float* dst, float v, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = v;
+}
+
+inline int ew_grid(int64_t total, int per_thread = 1) {
+  int64_t blocks = (total + (int64_t)EW_THREADS * per_thread - 1) / ((int64_t)EW_THREADS * per_thread);
+  const int64_t cap = 148 * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+inline int pixel_slabs(int64_t pixels, int chan_groups) {
+  int64_t want = (148 * 8) / (chan_groups > 0 ? chan_groups : 1);
+  int64_t maxs = (pixels + 7) / 8;
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  if (want > 65535) want = 65535;
+  return (int)want;
+}
+
+}  // namespace
+
+extern "C" {
+
+int icf_argmax_rows(const void* x, int32_t x_dtype, int32_t n, int32_t k, int32_t* out, void* stream) {
+  ICF_REQUIRE(x && out && n >= 0 && k >= 1 && x_dtype >= 0 && x_dtype <= 3, "icf_argmax_rows: bad arguments");
+  if (n == 0) return 0;
+  argmax_rows_kernel<<<icf::cdiv(n, 128), 128, 0, icf::as_stream(stream)>>>(x, x_dtype, n, k, out);
+  return icf::check_launch("argmax_rows");
+}
+
+int icf_image_features_fwd(const icf_imgfeat_args* a, void* stream) {
+  ICF_REQUIRE(a && a->x && a->feat, "icf_image_features_fwd: null pointer");
+  ICF_REQUIRE(a->n_emb >= 0 && a->n_cont >= 0 && a->n_emb <= ICF_MAX_PLANES && a->n_cont <= ICF_MAX_PLANES &&
+                  1 + a->n_emb + a->n_cont <= a->feat_pitch,
+              "icf_image_features_fwd: %d emb + %d cont planes do not fit pitch %d", a->n_emb, a->n_cont,
+              a->feat_pitch);
+  const int64_t total = (int64_t)a->N * a->H * a->W;
+  if (total == 0) return 0;
+  imgfeat_fwd_kernel<<<icf::cdiv(total, EW_THREADS), EW_THREADS, 0, icf::as_stream(stream)>>>(*a);
+  return icf::check_launch("imgfeat_fwd");
+}
+
+int icf_image_features_bwd(const icf_imgfeat_args* a, void* stream) {
+  ICF_REQUIRE(a && a->dfeat, "icf_image_features_bwd: null pointer");
+  if (a->n_emb == 0 || a->N == 0) return 0;
+  const int64_t warps = (int64_t)a->N * a->n_emb * 256;
+  imgfeat_bwd_kernel<<<icf::cdiv(warps * 32, EW_THREADS), EW_THREADS, 0, icf::as_stream(stream)>>>(*a);
+  return icf::check_launch("imgfeat_bwd");
+}
+
+int icf_latent_features_fwd(const icf_latfeat_args* a, void* stream) {
+  ICF_REQUIRE(a && a->z && a->feat, "icf_latent_features_fwd: null pointer");
+  ICF_REQUIRE(a->latent + 256 * a->n_emb + a->n_cont <= a->feat_pitch,
+              "icf_latent_features_fwd: feature row %d > pitch %d", a->latent + 256 * a->n_emb + a->n_cont,
+              a->feat_pitch);
+  const int64_t total = (int64_t)a->N * a->feat_pitch;
+  if (total == 0) return 0;
+  latfeat_fwd_kernel<<<icf::cdiv(total, EW_THREADS), EW_THREADS, 0, icf::as_stream(stream)>>>(*a);
+  return icf::check_launch("latfeat_fwd");
+}
+
+int icf_latent_features_bwd(const icf_latfeat_args* a, void* stream) {
+  ICF_REQUIRE(a && a->dfeat, "icf_latent_features_bwd: null pointer");
+  if (a->N == 0) return 0;
+  cudaStream_t st = icf::as_stream(stream);
+  int tot_k = 0;
+  bool any_row = a->dz != nullptr;
+  for (int e = 0; e < a->n_emb; ++e) { tot_k += a->emb_k[e]; any_row = any_row || a->donehot[e]; }
+  for (int e = 0; e < a->n_cont; ++e) any_row = any_row || a->dcont[e];
+  if (any_row) {
+    const int64_t total = (int64_t)a->N * (a->latent + a->n_cont + tot_k);
+    latfeat_bwd_rows_kernel<<<icf::cdiv(total, EW_THREADS), EW_THREADS, 0, st>>>(*a);
+    if (int r = icf::check_launch("latfeat_bwd_rows")) return r;
+  }
+  for (int e = 0; e < a->n_emb; ++e) {
+    if (!a->demb_table[e]) continue;
+    latfeat_bwd_table_kernel<<<a->emb_k[e], 256, 0, st>>>(*a, e);
+    if (int r = icf::check_launch("latfeat_bwd_table")) return r;
+  }
+  return 0;
+}
+
+int icf_bn_finalize(float* stats, int32_t C, double count, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                    float* scale, float* shift, float* save_mean, float* save_invstd, void* stream) {
+  ICF_REQUIRE(stats && scale && shift && C > 0 && count > 0, "icf_bn_finalize: bad arguments");
+  bn_finalize_kernel<<<icf::cdiv(C, 128), 128, 0, icf::as_stream(stream)>>>(
+      stats, C, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, scale,
+      shift, save_mean, save_invstd);
+  return icf::check_launch("bn_finalize");
+}
+
+int icf_scale_shift_mask(const void* y, int32_t y_dtype, int32_t y_pitch, void* u, int32_t u_dtype,
+                         int32_t u_pitch, int64_t pixels, int32_t pixels_per_sample, int32_t C,
+                         const float* scale, const float* shift, const float* mask, int32_t mask_pitch,
+                         void* stream) {
+  ICF_REQUIRE(y && u && C > 0 && pixels_per_sample > 0, "icf_scale_shift_mask: bad arguments");
+  if (pixels == 0) return 0;
+  scale_shift_mask_kernel<<<ew_grid(pixels * C, 4), EW_THREADS, 0, icf::as_stream(stream)>>>(
+      y, y_dtype, y_pitch, u, u_dtype, u_pitch, pixels, pixels_per_sample, C, scale, shift, mask, mask_pitch);
+  return icf::check_launch("scale_shift_mask");
+}
+
+int icf_bn_bwd_reduce(const void* dU, int32_t d_dtype, int32_t d_pitch, const void* y, int32_t y_dtype,
+                      int32_t y_pitch, int64_t pixels, int32_t pixels_per_sample, int32_t C, const float* mask,
+                      int32_t mask_pitch, const float* save_mean, const float* save_invstd, float* sums,
+                      void* stream) {
+  ICF_REQUIRE(dU && y && save_mean && save_invstd && sums && C > 0, "icf_bn_bwd_reduce: bad arguments");
+  if (pixels == 0) return 0;
+  const int groups = icf::cdiv(C, 32);
+  dim3 grid(groups, pixel_slabs(pixels, groups));
+  bn_bwd_reduce_kernel<<<grid, 256, 0, icf::as_stream(stream)>>>(dU, d_dtype, d_pitch, y, y_dtype, y_pitch,
+                                                                   pixels, pixels_per_sample, C, mask,
+                                                                   mask_pitch, save_mean, save_invstd, sums);
+  return icf::check_launch("bn_bwd_reduce");
+}
+
+int icf_act_backward(const icf_actbwd_args* a, void* stream) {
+  ICF_REQUIRE(a && a->dOut && a->y && a->dPre && a->C > 0 && a->pixels_per_sample > 0,
+              "icf_act_backward: bad arguments");
+  if (a->bn_sums)
+    ICF_REQUIRE(a->bn_gamma && a->bn_mean && a->bn_invstd, "icf_act_backward: incomplete BatchNorm state");
+  if (a->pixels == 0) return 0;
+  const int groups = icf::cdiv(a->C, 32);
+  dim3 grid(groups, pixel_slabs(a->pixels, groups));
+  act_backward_kernel<<<grid, 256, 0, icf::as_stream(stream)>>>(*a);
+  return icf::check_launch("act_backward");
+}
+
+int icf_bce_logits(const void* logits, int32_t l_dtype, int32_t l_pitch, int32_t n, float target, float weight,
+                   float* loss_out, void* dlogits, int32_t d_dtype, int32_t d_pitch, void* stream) {
+  ICF_REQUIRE(logits && n > 0, "icf_bce_logits: bad arguments");
+  bce_logits_kernel<<<1, 1024, 0, icf::as_stream(stream)>>>(logits, l_dtype, l_pitch, n, target, weight,
+                                                            loss_out, dlogits, d_dtype, d_pitch);
+  return icf::check_launch("bce_logits");
+}
+
+int icf_sigmoid_mean(const void* logits, int32_t l_dtype, int32_t l_pitch, int32_t n, float* score_out,
+                     void* stream) {
+  ICF_REQUIRE(logits && score_out && n > 0, "icf_sigmoid_mean: bad arguments");
+  sigmoid_mean_kernel<<<1, 1024, 0, icf::as_stream(stream)>>>(logits, l_dtype, l_pitch, n, score_out);
+  return icf::check_launch("sigmoid_mean");
+}
+
+int icf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float* state,
+                  void* stream) {
+  ICF_REQUIRE(param && grad && exp_avg && exp_avg_sq && state && n >= 0, "icf_adam_step: bad arguments");
+  ICF_REQUIRE((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
+               reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) % 16 == 0,
+              "icf_adam_step: buffers must be 16-byte aligned");
+  cudaStream_t st = icf::as_stream(stream);
+  adam_tick_kernel<<<1, 1, 0, st>>>(state);
+  if (n > 0) adam_kernel<<<ew_grid(n, 4), EW_THREADS, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, state);
+  return icf::check_launch("adam");
+}
+
+int icf_pack(const float* src, void* dst, int32_t dst_dtype, const icf_perm* p, void* stream) {
+  ICF_REQUIRE(src && dst && p && p->d2_pad >= p->d2 && p->d0_pad >= p->d0, "icf_pack: bad arguments");
+  const int64_t total = p->d0_pad * p->d1 * p->d2_pad;
+  if (total == 0) return 0;
+  pack_kernel<<<ew_grid(total), EW_THREADS, 0, icf::as_stream(stream)>>>(src, dst, dst_dtype, *p);
+  return icf::check_launch("pack");
+}
+
+int icf_unpack(const float* src_packed, float* dst, const icf_perm* p, int32_t atomic_add, void* stream) {
+  ICF_REQUIRE(src_packed && dst && p, "icf_unpack: bad arguments");
+  const int64_t total = p->d0 * p->d1 * p->d2;
+  if (total == 0) return 0;
+  unpack_kernel<<<ew_grid(total), EW_THREADS, 0, icf::as_stream(stream)>>>(src_packed, dst, *p, atomic_add);
+  return icf::check_launch("unpack");
+}
+
+int icf_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream) {
+  ICF_REQUIRE(src && dst && n >= 0, "icf_cast: bad arguments");
+  if (n == 0) return 0;
+  cast_kernel<<<ew_grid(n, 4), EW_THREADS, 0, icf::as_stream(stream)>>>(src, src_dtype, dst, dst_dtype, n);
+  return icf::check_launch("cast");
+}
+
+int icf_fill_f32(float* dst, float value, int64_t n, void* stream) {
+  ICF_REQUIRE(dst && n >= 0, "icf_fill_f32: bad arguments");
+  if (n == 0) return 0;
+  fill_kernel<<<ew_grid(n, 4), EW_THREADS, 0, icf::as_stream(stream)>>>(dst, value, n);
+  return icf::check_launch("fill");
+}
+
+}  // extern "C"

@@ -1,0 +1,547 @@
+"""Execution engine of the conditional-BiGAN hot path on raw NHWC buffers.
+
+One ``NetExec`` runs one network (Encoder / Generator / Discriminator) of one family (icf_b200.arch) through
+the C-ABI kernels: attribute/latent feature assembly -> towers of fused conv layers (bias + activation +
+Dropout2d mask + BatchNorm statistics in the conv epilogue, BatchNorm apply + Dropout2d in one pass) and the
+matching backward (fused activation/dropout/BatchNorm backward, dgrad, wgrad).  It replaces the forward /
+autograd of the reference modules image_scms/mnist.py:21-154, audio_mnist.py:173-318, whalecalls.py:230-387,
+esrf_acoustic.py:134-260.
+
+Layout: activations are 2-D tensors [N*H*W, pitch] (NHWC, pitch = channels rounded up to 8) in the compute
+dtype (fp32 or bf16); parameters stay fp32 in the checkpoint layout on the owning nn.Module and are re-packed
+into K-major operand copies ([rows][tap][channels]) by ``repack()``.
+"""
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .arch import Family, L, conv_out, convT_out, pad8
+
+F32, BF16 = ops.F32, ops.BF16
+
+
+def dtype_code(name) -> int:
+    if name in (F32, "fp32", "f32", "float32", torch.float32):
+        return F32
+    if name in (BF16, "bf16", "bfloat16", torch.bfloat16):
+        return BF16
+    raise ValueError(f"compute dtype must be 'fp32' or 'bf16', got {name!r}")
+
+
+class Act:
+    """An NHWC activation: 2-D tensor [N*H*W, pitch] plus a channel offset / count inside the pitch."""
+    __slots__ = ("t", "off", "C")
+
+    def __init__(self, t, C, off=0):
+        self.t, self.C, self.off = t, C, off
+
+    @property
+    def pitch(self):
+        return self.t.shape[1]
+
+    @property
+    def ptr(self):
+        return ops.ptr(self.t, self.off)
+
+    @property
+    def code(self):
+        return ops.code_of(self.t)
+
+
+class LayerExec:
+    """One conv-shaped contraction with its packed operands (Conv2d / ConvTranspose2d / Linear+Unflatten)."""
+
+    def __init__(self, spec: L, hin: int, win: int, code: int, device):
+        self.spec, self.code, self.device = spec, code, device
+        self.Hin, self.Win = hin, win
+        if spec.kind == "conv":
+            self.form, self.taps_r = ops.GATHER, spec.k
+            self.P, self.Q = conv_out(hin, spec.k, spec.stride, spec.pad), conv_out(win, spec.k, spec.stride, spec.pad)
+            self.Cin, self.Kout = spec.cin, spec.cout
+            self.Hout, self.Wout, self.Cout = self.P, self.Q, spec.cout
+        elif spec.kind == "convT":
+            self.form, self.taps_r = ops.TRANSPOSED, spec.k
+            self.P = convT_out(hin, spec.k, spec.stride, spec.pad, spec.opad)
+            self.Q = convT_out(win, spec.k, spec.stride, spec.pad, spec.opad)
+            self.Cin, self.Kout = spec.cin, spec.cout
+            self.Hout, self.Wout, self.Cout = self.P, self.Q, spec.cout
+        elif spec.kind == "linear":
+            # nn.Linear + nn.Unflatten(1,(Cu,Hu,Wu)) as one GEMM whose output columns are permuted to
+            # NHWC order: column (h*Wu+w)*Cu + c  <-  reference row c*Hu*Wu + h*Wu + w
+            assert hin == 1 and win == 1 and spec.unflatten is not None
+            cu, hu, wu = spec.unflatten
+            assert cu * hu * wu == spec.cout
+            self.form, self.taps_r = ops.GATHER, 1
+            self.P = self.Q = 1
+            self.Cin, self.Kout = spec.cin, spec.cout
+            self.Hout, self.Wout, self.Cout = hu, wu, cu
+        else:
+            raise ValueError(spec.kind)
+        self.R = self.S = self.taps_r
+        self.taps = self.R * self.S
+        self.stride = spec.stride if spec.kind != "linear" else 1
+        self.pad = spec.pad if spec.kind != "linear" else 0
+        self.in_pitch_min = pad8(self.Cin)
+        self.wf_pitch = pad8(self.Cin)
+        self.wb_pitch = pad8(self.Kout)
+        dt = ops.torch_dtype(code)
+        self.w_fwd = torch.zeros(self.Kout * self.taps * self.wf_pitch, dtype=dt, device=device)
+        self.w_bwd = torch.zeros(self.Cin * self.taps * self.wb_pitch, dtype=dt, device=device)
+        self.bias = torch.zeros(self.Kout, dtype=torch.float32, device=device)
+        C_, K_, T = self.Cin, self.Kout, self.taps
+        if spec.kind == "conv":          # reference weight [K][C][R][S]
+            self.perm_f = ops.make_perm(K_, T, C_, C_ * T, 1, T, d2_pad=self.wf_pitch)
+            self.perm_b = ops.make_perm(C_, T, K_, T, 1, C_ * T, d2_pad=self.wb_pitch)
+            self.perm_g = ops.make_perm(K_, T, C_, C_ * T, 1, T)                 # dw packed [K][T][C]
+            self.perm_bias = None
+        elif spec.kind == "convT":       # reference weight [C][K][R][S]
+            self.perm_f = ops.make_perm(K_, T, C_, T, 1, K_ * T, d2_pad=self.wf_pitch)
+            self.perm_b = ops.make_perm(C_, T, K_, K_ * T, 1, T, d2_pad=self.wb_pitch)
+            self.perm_g = ops.make_perm(C_, T, K_, K_ * T, 1, T)                 # dw packed [C][T][K]
+            self.perm_bias = None
+        else:                            # reference weight [Cu*HW][C]
+            cu, hu, wu = spec.unflatten
+            hw = hu * wu
+            self.perm_f = ops.make_perm(hw, cu, C_, C_, hw * C_, 1, d2_pad=self.wf_pitch)
+            self.perm_b = ops.make_perm(C_, hw, cu, 1, C_, hw * C_)
+            self.wb_pitch = K_
+            self.w_bwd = torch.zeros(self.Cin * K_, dtype=dt, device=device)
+            self.perm_g = ops.make_perm(hw, cu, C_, C_, hw * C_, 1)              # dw packed [hw*cu][C]
+            self.perm_bias = ops.make_perm(1, hw, cu, 0, 1, hw)
+        self.wgrad_elems = self.Kout * self.taps * self.Cin
+
+    # ---- operands -------------------------------------------------------------------------------
+    def repack(self, weight: torch.Tensor, bias: torch.Tensor):
+        ops.pack(weight.data_ptr(), self.w_fwd.data_ptr(), self.code, self.perm_f)
+        ops.pack(weight.data_ptr(), self.w_bwd.data_ptr(), self.code, self.perm_b)
+        if self.perm_bias is None:
+            ops.cast(bias.data_ptr(), F32, self.bias.data_ptr(), F32, self.Kout)
+        else:
+            ops.pack(bias.data_ptr(), self.bias.data_ptr(), F32, self.perm_bias)
+
+    # ---- launches -------------------------------------------------------------------------------
+    def forward(self, N, x: Act, y: Act, mask=None, mask_pitch=0, stats=None, out_f32=False):
+        sp = self.spec
+        ops.conv_forward(self.code, self.form, N, self.Hin, self.Win, self.Cin, x.pitch,
+                         self.P, self.Q, self.Kout, y.pitch if sp.kind != "linear" else y.pitch * self.Hout * self.Wout,
+                         self.R, self.S, self.stride, self.pad, x.ptr, self.w_fwd.data_ptr(), self.Kout,
+                         self.wf_pitch, y.ptr, bias=self.bias.data_ptr(), act=sp.act, slope=sp.slope,
+                         out_f32=out_f32, mask=mask, mask_pitch=mask_pitch, stats=stats)
+
+    def dgrad(self, N, dpre: Act, dx: Act):
+        """dx[n,h,w,c] = sum_{k,taps} dpre[...]*w  — the other conv form with the transposed operand."""
+        form = ops.TRANSPOSED if self.form == ops.GATHER else ops.GATHER
+        lin = self.spec.kind == "linear"
+        dp_pitch = dpre.pitch * self.Hout * self.Wout if lin else dpre.pitch
+        ops.conv_forward(self.code, form, N, self.P, self.Q, self.Kout, dp_pitch,
+                         self.Hin, self.Win, self.Cin, dx.pitch, self.R, self.S, self.stride, self.pad,
+                         dpre.ptr, self.w_bwd.data_ptr(), self.Cin, self.wb_pitch, dx.ptr)
+
+    def wgrad(self, N, dpre: Act, x: Act, gw: torch.Tensor, scratch: torch.Tensor):
+        """gw (checkpoint layout, fp32) = weight gradient; ``scratch`` holds the packed fp32 accumulator."""
+        n = self.wgrad_elems
+        ops.fill_f32(scratch.data_ptr(), 0.0, n)
+        lin = self.spec.kind == "linear"
+        dp_pitch = dpre.pitch * self.Hout * self.Wout if lin else dpre.pitch
+        if self.spec.kind == "convT":     # small = X (A = Cin), big = dY (B = Cout)
+            ops.conv_wgrad(self.code, N, self.Hin, self.Win, self.Cin, x.pitch, self.P, self.Q, self.Kout,
+                           dp_pitch, self.R, self.S, self.stride, self.pad, x.ptr, dpre.ptr, scratch.data_ptr())
+        else:                             # small = dY (A = Cout), big = X (B = Cin)
+            ops.conv_wgrad(self.code, N, self.P, self.Q, self.Kout, dp_pitch, self.Hin, self.Win, self.Cin,
+                           x.pitch, self.R, self.S, self.stride, self.pad, dpre.ptr, x.ptr, scratch.data_ptr())
+        ops.unpack(scratch.data_ptr(), gw.data_ptr(), self.perm_g)
+
+
+def mask_sites(fam: Family):
+    """[(tower, layer index, 'in'|'out'|'bn', p, channels)] of the Discriminator's Dropout2d sites in the order
+    torch consumes the RNG: dx, then dz, then dxz (mnist.py:151-154), Sequential order inside each."""
+    sites = []
+    for tname in ("Dx", "Dz", "Dxz"):
+        for i, l in enumerate(getattr(fam, tname)):
+            if l.in_drop:
+                sites.append((tname, i, "in", l.in_drop, l.cin))
+            if l.out_drop:
+                sites.append((tname, i, "out", l.out_drop, l.cout))
+            if l.bn_drop:
+                sites.append((tname, i, "bn", l.bn_drop, l.cout))
+    return sites
+
+
+def draw_masks(fam: Family, n: int, device) -> List[torch.Tensor]:
+    """Dropout2d masks of ONE Discriminator forward, drawn with the aten calls nn.Dropout2d makes on a 4-D
+    input (feature_dropout: ``empty(N,C,1,1).bernoulli_(1-p).div_(1-p)``) in the reference's order, so that
+    the same seed yields the same masks as the reference on the same device."""
+    return [torch.empty(n, c, 1, 1, device=device).bernoulli_(1 - p).div_(1 - p)
+            for (_, _, _, p, c) in mask_sites(fam)]
+
+
+class Tower:
+    def __init__(self, specs, hin, win, code, device):
+        self.layers: List[LayerExec] = []
+        h, w = hin, win
+        for s in specs:
+            le = LayerExec(s, h, w, code, device)
+            self.layers.append(le)
+            h, w = le.Hout, le.Wout
+        self.Hout, self.Wout = h, w
+        self.code, self.device = code, device
+        # BatchNorm statistic accumulators, zero between uses (icf_bn_finalize clears them)
+        self.stats = {i: torch.zeros(2 * le.Kout, dtype=torch.float32, device=device)
+                      for i, le in enumerate(self.layers) if le.spec.bn}
+
+
+class NetExec:
+    """Runs one network of a family.  ``module`` owns the fp32 parameters / buffers (checkpoint layout)."""
+
+    def __init__(self, fam: Family, role: str, module, code: int, device):
+        assert role in ("E", "G", "D")
+        self.fam, self.role, self.module, self.code, self.device = fam, role, module, code, device
+        self.dt = ops.torch_dtype(code)
+        H, W = fam.image
+        self.H, self.W = H, W
+        self.n_emb, self.n_cont = len(fam.cat_attrs), len(fam.cont_attrs)
+        self.feat_ch = 1 + self.n_emb + self.n_cont
+        if role == "E":
+            self.towers = {"E": Tower(fam.E, H, W, code, device)}
+        elif role == "G":
+            self.towers = {"G": Tower(fam.G, 1, 1, code, device)}
+            self.lat_dim = fam.latent + 256 * self.n_emb + self.n_cont
+            assert self.lat_dim == fam.G[0].cin, (self.lat_dim, fam.G[0].cin)
+        else:
+            self.towers = {"Dx": Tower(fam.Dx, H, W, code, device), "Dz": Tower(fam.Dz, 1, 1, code, device),
+                           "Dxz": Tower(fam.Dxz, 1, 1, code, device)}
+            self.sites = mask_sites(fam)
+        self._versions = None
+        self._scratch = None
+        self.emb_key = 2 if role != "G" else 3      # index into fam.cat_attrs tuples
+
+    # ---- parameters -----------------------------------------------------------------------------
+    def tensors(self) -> Dict[str, torch.Tensor]:
+        d = dict(self.module.named_parameters())
+        d.update(dict(self.module.named_buffers()))
+        return d
+
+    def all_layers(self):
+        for t in self.towers.values():
+            for le in t.layers:
+                yield le
+
+    def repack(self, force=False):
+        """Refresh the packed operand copies if any parameter changed (tracked by tensor version)."""
+        ts = self.tensors()
+        vers = tuple((k, v._version, v.data_ptr()) for k, v in ts.items() if k.endswith(("weight", "bias")))
+        if not force and vers == self._versions:
+            return
+        for le in self.all_layers():
+            le.repack(ts[le.spec.key + ".weight"], ts[le.spec.key + ".bias"])
+        self._versions = vers
+
+    def scratch(self):
+        if self._scratch is None:
+            n = max(le.wgrad_elems for le in self.all_layers())
+            self._scratch = torch.empty(n, dtype=torch.float32, device=self.device)
+        return self._scratch
+
+    def new_grads(self) -> Dict[str, torch.Tensor]:
+        return {k: torch.zeros_like(v) for k, v in self.module.named_parameters()}
+
+    # ---- tower forward / backward ---------------------------------------------------------------
+    def _tower_fwd(self, tname, N, x: Act, masks: Dict, training: bool, save: bool, final: Optional[Act] = None,
+                   final_mask=None, final_f32=False):
+        """masks: {(layer index, 'out'|'bn'): tensor [N,C]}.  Returns (output Act, saved list)."""
+        tw = self.towers[tname]
+        ts = self.tensors()
+        saved = []
+        n_layers = len(tw.layers)
+        for i, le in enumerate(tw.layers):
+            sp = le.spec
+            last = i == n_layers - 1
+            pix = N * le.Hout * le.Wout
+            if last and final is not None:
+                y = final
+            else:
+                ydt = torch.float32 if (last and final_f32) else self.dt
+                y = Act(torch.empty((pix, pad8(le.Cout) if le.Cout > 1 else 1), dtype=ydt, device=self.device), le.Cout)
+            om = masks.get((i, "out"))
+            om_ptr, om_pitch = (ops.ptr(om), om.shape[1]) if om is not None else (None, 0)
+            if last and final_mask is not None:
+                assert om is None
+                fm, fm_off = final_mask
+                om, om_ptr, om_pitch = fm, ops.ptr(fm, fm_off), fm.shape[1]
+            use_stats = sp.bn is not None and training
+            stats = tw.stats[i].data_ptr() if use_stats else None
+            le.forward(N, x, y, mask=om_ptr, mask_pitch=om_pitch, stats=stats,
+                       out_f32=(y.t.dtype == torch.float32 and self.code == BF16))
+            rec = {"x": x, "y": y, "out_mask": (om, om_ptr, om_pitch) if om is not None else None, "bn": None}
+            nxt = y
+            if sp.bn is not None:
+                K = le.Kout
+                gamma, beta = ts[sp.bn + ".weight"], ts[sp.bn + ".bias"]
+                rm, rv = ts[sp.bn + ".running_mean"], ts[sp.bn + ".running_var"]
+                ss = torch.empty(4 * K, dtype=torch.float32, device=self.device)   # scale|shift|mean|invstd
+                if training:
+                    nbt = ts.get(sp.bn + ".num_batches_tracked")
+                    ops.bn_finalize(stats, K, pix, gamma.data_ptr(), beta.data_ptr(), 1e-5, 0.1, rm.data_ptr(),
+                                    rv.data_ptr(), ops.ptr(nbt), ops.ptr(ss), ops.ptr(ss, K), ops.ptr(ss, 2 * K),
+                                    ops.ptr(ss, 3 * K))
+                else:
+                    # eval mode: affine transform from the running statistics (tiny per-channel vectors)
+                    inv = torch.rsqrt(rv + 1e-5)
+                    ss[:K] = gamma * inv
+                    ss[K:2 * K] = beta - rm * gamma * inv
+                    ss[2 * K:3 * K] = rm
+                    ss[3 * K:] = inv
+                bm = masks.get((i, "bn"))
+                u = Act(torch.empty((pix, y.pitch), dtype=self.dt, device=self.device), le.Cout)
+                ops.scale_shift_mask(y.ptr, y.code, y.pitch, u.ptr, u.code, u.pitch, pix, le.Hout * le.Wout, K,
+                                     scale=ops.ptr(ss), shift=ops.ptr(ss, K), mask=ops.ptr(bm),
+                                     mask_pitch=bm.shape[1] if bm is not None else 0)
+                rec["bn"] = {"ss": ss, "mask": bm, "training": training}
+                nxt = u
+            if save:
+                saved.append(rec)
+            x = nxt
+        return x, saved
+
+    def _tower_bwd(self, tname, N, saved, dout: Act, grads: Optional[Dict], need_dx: bool, inplace_ok=True):
+        """dout: gradient w.r.t. the tower's (consumer visible) output.  Returns dX Act of the tower input or None."""
+        tw = self.towers[tname]
+        ts = self.tensors()
+        g = dout
+        for i in range(len(tw.layers) - 1, -1, -1):
+            le, rec = tw.layers[i], saved[i]
+            sp = le.spec
+            y, x = rec["y"], rec["x"]
+            pix = N * le.Hout * le.Wout
+            pps = le.Hout * le.Wout
+            K = le.Kout if sp.kind != "linear" else le.Cout
+            Kfull = le.Kout
+            # for Linear+Unflatten the activation tensor is [N*hw, Cu]; treat it as [N, hw*Cu] rows
+            if sp.kind == "linear":
+                a_pix, a_pps, a_C = N, 1, Kfull
+                ypitch, gpitch = y.pitch * pps, g.pitch * pps
+            else:
+                a_pix, a_pps, a_C = pix, pps, K
+                ypitch, gpitch = y.pitch, g.pitch
+            bn = rec["bn"]
+            kw = {}
+            if bn is not None:
+                if not bn["training"]:
+                    raise RuntimeError("backward through an eval-mode BatchNorm2d is not part of the hot path")
+                ss, bm = bn["ss"], bn["mask"]
+                sums = torch.zeros(2 * K, dtype=torch.float32, device=self.device)
+                bm_ptr, bm_pitch = (ops.ptr(bm), bm.shape[1]) if bm is not None else (None, 0)
+                ops.bn_bwd_reduce(g.ptr, g.code, g.pitch, y.ptr, y.code, y.pitch, pix, pps, K, bm_ptr, bm_pitch,
+                                  ops.ptr(ss, 2 * K), ops.ptr(ss, 3 * K), sums.data_ptr())
+                kw = dict(bn_sums=sums.data_ptr(), bn_mask=bm_ptr, bn_mask_pitch=bm_pitch,
+                          bn_gamma=ts[sp.bn + ".weight"].data_ptr(), bn_mean=ops.ptr(ss, 2 * K),
+                          bn_invstd=ops.ptr(ss, 3 * K),
+                          bn_dgamma=ops.ptr(grads[sp.bn + ".weight"]) if grads is not None else None,
+                          bn_dbeta=ops.ptr(grads[sp.bn + ".bias"]) if grads is not None else None)
+            om = rec["out_mask"]
+            om_ptr, om_pitch = (om[1], om[2]) if om is not None else (None, 0)
+            # dPre in the compute dtype; reuse g's storage when it is ours, same dtype and same pitch
+            if inplace_ok and g.t.dtype == self.dt and g.off == 0 and g.pitch == (pad8(le.Cout) if le.Cout > 1 else 1):
+                dpre = Act(g.t, le.Cout)
+            else:
+                dpre = Act(torch.empty((pix, pad8(le.Cout) if le.Cout > 1 else 1), dtype=self.dt, device=self.device),
+                           le.Cout)
+            dpitch = dpre.pitch * pps if sp.kind == "linear" else dpre.pitch
+            if grads is not None:
+                if le.perm_bias is None:
+                    dbias_t = grads[sp.key + ".bias"]
+                else:
+                    dbias_t = torch.zeros(Kfull, dtype=torch.float32, device=self.device)
+                dbias = dbias_t.data_ptr()
+            else:
+                dbias_t, dbias = None, None
+            ops.act_backward(g.ptr, g.code, gpitch, y.ptr, y.code, ypitch, dpre.ptr, dpre.code, dpitch, a_pix, a_pps,
+                             a_C, sp.act, sp.slope, out_mask=om_ptr, mask_pitch=om_pitch, dbias=dbias, **kw)
+            if grads is not None:
+                if le.perm_bias is not None:
+                    ops.unpack(dbias_t.data_ptr(), grads[sp.key + ".bias"].data_ptr(), le.perm_bias)
+                le.wgrad(N, dpre, x, grads[sp.key + ".weight"], self.scratch())
+            if i > 0 or need_dx:
+                dx = Act(torch.empty((N * le.Hin * le.Win, x.pitch), dtype=self.dt, device=self.device), le.Cin)
+                le.dgrad(N, dpre, dx)
+                g = dx
+            else:
+                g = None
+            inplace_ok = True
+        return g
+
+    # ---- attribute plumbing ---------------------------------------------------------------------
+    def _attr_inputs(self, c: Dict[str, torch.Tensor], N):
+        """-> (onehot float tensors per categorical attr, continuous float tensors (N,))."""
+        cats, conts = [], []
+        for (name, K, _, _) in self.fam.cat_attrs:
+            if name not in c:
+                raise KeyError(f"attribute {name!r} missing from the attribute dict")
+            t = c[name]
+            ops.require_cuda(t)
+            if t.shape != (N, K):
+                raise ValueError(f"attribute {name!r}: expected shape {(N, K)}, got {tuple(t.shape)}")
+            cats.append(t)
+        for name in self.cont_names(c):
+            t = c[name]
+            ops.require_cuda(t)
+            if t.numel() != N:
+                raise ValueError(f"attribute {name!r}: expected {N} values, got shape {tuple(t.shape)}")
+            conts.append(t.detach().reshape(N).float().contiguous())
+        return cats, conts
+
+    def cont_names(self, c):
+        """Continuous attribute order.  MorphoMNIST treats every key != 'digit' as continuous, in sorted order
+        (mnist.py:47-55); the other families name theirs explicitly."""
+        if self.fam.name == "mnist":
+            names = sorted(k for k in c if k != "digit")
+            if len(names) != self.n_cont:
+                raise ValueError(f"expected {self.n_cont} continuous attributes, got {names}")
+            return names
+        return list(self.fam.cont_attrs)
+
+    def _image_feats(self, N, x_ptr, x_code, x_pitch, c, mask):
+        ts = self.tensors()
+        cats, conts = self._attr_inputs(c, N)
+        idx = [ops.argmax_rows(t.detach()) for t in cats]
+        tables = [ts[a[self.emb_key]] for a in self.fam.cat_attrs]
+        feat = Act(torch.empty((N * self.H * self.W, pad8(self.feat_ch)), dtype=self.dt, device=self.device),
+                   self.feat_ch)
+        ops.image_features(self.code, N, self.H, self.W, feat.pitch, x_ptr, x_code, x_pitch,
+                           [t.data_ptr() for t in tables], [t.data_ptr() for t in idx],
+                           [t.data_ptr() for t in conts], ops.ptr(mask), mask.shape[1] if mask is not None else 0,
+                           feat.ptr)
+        return feat, {"idx": idx, "conts": conts, "mask": mask}
+
+    def _image_feats_bwd(self, N, fstate, dfeat: Act, grads):
+        ts = self.tensors()
+        tables = [ts[a[self.emb_key]] for a in self.fam.cat_attrs]
+        dtables = [grads[a[self.emb_key]] for a in self.fam.cat_attrs]
+        mask = fstate["mask"]
+        ops.image_features(self.code, N, self.H, self.W, dfeat.pitch, None, F32, 1,
+                           [t.data_ptr() for t in tables], [t.data_ptr() for t in fstate["idx"]],
+                           [t.data_ptr() for t in fstate["conts"]], ops.ptr(mask),
+                           mask.shape[1] if mask is not None else 0, None, dfeat=dfeat.ptr,
+                           dtables=[t.data_ptr() for t in dtables], backward=True)
+
+    def _dX_from_dfeat(self, N, dfeat: Act, mask):
+        """Gradient w.r.t. the image channel: dfeat[..., 0] * mask[n, 0] -> fp32 [N*H*W, 1]."""
+        pix = N * self.H * self.W
+        dX = torch.empty((pix, 1), dtype=torch.float32, device=self.device)
+        ops.scale_shift_mask(dfeat.ptr, dfeat.code, dfeat.pitch, dX.data_ptr(), F32, 1, pix, self.H * self.W, 1,
+                             mask=ops.ptr(mask), mask_pitch=mask.shape[1] if mask is not None else 0)
+        return dX
+
+    # ---- Encoder --------------------------------------------------------------------------------
+    def encoder_forward(self, N, x_ptr, x_code, x_pitch, c, save=True):
+        self.repack()
+        feat, fstate = self._image_feats(N, x_ptr, x_code, x_pitch, c, None)
+        out, saved = self._tower_fwd("E", N, feat, {}, True, save)
+        return out, {"N": N, "feat": fstate, "tower": saved}
+
+    def encoder_backward(self, st, dout: Act, grads, need_dX=False):
+        N = st["N"]
+        need_feat = need_dX or (grads is not None and self.n_emb > 0)
+        dfeat = self._tower_bwd("E", N, st["tower"], dout, grads, need_feat, inplace_ok=False)
+        if dfeat is None:
+            return None
+        if grads is not None and self.n_emb > 0:
+            self._image_feats_bwd(N, st["feat"], dfeat, grads)
+        return self._dX_from_dfeat(N, dfeat, None) if need_dX else None
+
+    # ---- Generator ------------------------------------------------------------------------------
+    def generator_forward(self, N, z_ptr, z_code, z_pitch, c, save=True):
+        self.repack()
+        ts = self.tensors()
+        cats, conts = self._attr_inputs(c, N)
+        onehots = [t.detach().float().contiguous() for t in cats]
+        tables = [ts[a[self.emb_key]] for a in self.fam.cat_attrs]
+        lat = Act(torch.empty((N, pad8(self.lat_dim)), dtype=self.dt, device=self.device), self.lat_dim)
+        ops.latent_features(self.code, N, self.fam.latent, lat.pitch, z_ptr, z_code, z_pitch,
+                            [a[1] for a in self.fam.cat_attrs], [t.data_ptr() for t in tables],
+                            [t.data_ptr() for t in onehots], [t.data_ptr() for t in conts], lat.ptr)
+        out, saved = self._tower_fwd("G", N, lat, {}, True, save)
+        return out, {"N": N, "onehots": onehots, "conts": conts, "tower": saved}
+
+    def generator_backward(self, st, dout: Act, grads, need_dz=False, need_dattr=False):
+        """-> (dz fp32 [N,latent] | None, [d_onehot per cat attr] | None, [d_cont per cont attr] | None)."""
+        N = st["N"]
+        need_lat = need_dz or need_dattr or (grads is not None and self.n_emb > 0)
+        dlat = self._tower_bwd("G", N, st["tower"], dout, grads, need_lat, inplace_ok=False)
+        if dlat is None:
+            return None, None, None
+        ts = self.tensors()
+        tables = [ts[a[self.emb_key]] for a in self.fam.cat_attrs]
+        dz = torch.empty((N, self.fam.latent), dtype=torch.float32, device=self.device) if need_dz else None
+        doh = [torch.empty_like(t) for t in st["onehots"]] if need_dattr else None
+        dco = [torch.empty_like(t) for t in st["conts"]] if need_dattr else None
+        dtab = [grads[a[self.emb_key]].data_ptr() for a in self.fam.cat_attrs] if grads is not None else []
+        ops.latent_features(self.code, N, self.fam.latent, dlat.pitch, None, F32, 0,
+                            [a[1] for a in self.fam.cat_attrs], [t.data_ptr() for t in tables],
+                            [t.data_ptr() for t in st["onehots"]], [t.data_ptr() for t in st["conts"]], None,
+                            dfeat=dlat.ptr, dz=ops.ptr(dz), dtables=dtab,
+                            donehots=[t.data_ptr() for t in doh] if doh else [],
+                            dconts=[t.data_ptr() for t in dco] if dco else [], backward=True)
+        return dz, doh, dco
+
+    # ---- Discriminator --------------------------------------------------------------------------
+    def discriminator_forward(self, N, x_ptr, x_code, x_pitch, z_ptr, z_code, z_pitch, c, masks=None,
+                              training=True, save=True):
+        """masks: list of (N,C,1,1)/(N,C) fp32 tensors in RNG order (draw_masks) or None to draw them here."""
+        self.repack()
+        fam = self.fam
+        per = {"Dx": {}, "Dz": {}, "Dxz": {}}
+        in_masks = {}
+        if training and self.sites:
+            if masks is None:
+                masks = draw_masks(fam, N, self.device)
+            if len(masks) != len(self.sites):
+                raise ValueError(f"expected {len(self.sites)} dropout masks, got {len(masks)}")
+            for (tname, i, where, _, ch), m in zip(self.sites, masks):
+                m = m.reshape(N, ch)
+                if m.dtype != torch.float32 or not m.is_contiguous():
+                    m = m.float().contiguous()
+                if where == "in":
+                    in_masks[tname] = m
+                else:
+                    per[tname][(i, where)] = m
+        feat, fstate = self._image_feats(N, x_ptr, x_code, x_pitch, c, in_masks.get("Dx"))
+        kx, kz = fam.Dx[-1].cout, fam.Dz[-1].cout
+        cat = torch.empty((N, kx + kz), dtype=self.dt, device=self.device)
+        cm = in_masks.get("Dxz")
+        _, sx = self._tower_fwd("Dx", N, feat, per["Dx"], training, save, final=Act(cat, kx, 0),
+                                final_mask=(cm, 0) if cm is not None else None)
+        zm = in_masks.get("Dz")
+        zin = Act(torch.empty((N, fam.latent), dtype=self.dt, device=self.device), fam.latent)
+        ops.scale_shift_mask(z_ptr, z_code, z_pitch, zin.ptr, zin.code, zin.pitch, N, 1, fam.latent,
+                             mask=ops.ptr(zm), mask_pitch=zm.shape[1] if zm is not None else 0)
+        _, sz = self._tower_fwd("Dz", N, zin, per["Dz"], training, save, final=Act(cat, kz, kx),
+                                final_mask=(cm, kx) if cm is not None else None)
+        logits, sxz = self._tower_fwd("Dxz", N, Act(cat, kx + kz), per["Dxz"], training, save, final_f32=True)
+        return logits, {"N": N, "feat": fstate, "Dx": sx, "Dz": sz, "Dxz": sxz, "zmask": zm, "cat": cat}
+
+    def discriminator_backward(self, st, dlogits: Act, grads, need_dX=False, need_dz=False):
+        """-> (dX fp32 [N*H*W,1] | None, dz fp32 [N,latent] | None)."""
+        N = st["N"]
+        fam = self.fam
+        kx, kz = fam.Dx[-1].cout, fam.Dz[-1].cout
+        dcat = self._tower_bwd("Dxz", N, st["Dxz"], dlogits, grads, True, inplace_ok=False)
+        dz = None
+        if need_dz or grads is not None:
+            dzin = self._tower_bwd("Dz", N, st["Dz"], Act(dcat.t, kz, kx), grads, need_dz, inplace_ok=False)
+            if need_dz:
+                zm = st["zmask"]
+                dz = torch.empty((N, fam.latent), dtype=torch.float32, device=self.device)
+                ops.scale_shift_mask(dzin.ptr, dzin.code, dzin.pitch, dz.data_ptr(), F32, fam.latent, N, 1,
+                                     fam.latent, mask=ops.ptr(zm), mask_pitch=zm.shape[1] if zm is not None else 0)
+        dX = None
+        if need_dX or grads is not None:
+            need_feat = need_dX or (grads is not None and self.n_emb > 0)
+            dfeat = self._tower_bwd("Dx", N, st["Dx"], Act(dcat.t, kx, 0), grads, need_feat, inplace_ok=False)
+            if dfeat is not None:
+                if grads is not None and self.n_emb > 0:
+                    self._image_feats_bwd(N, st["feat"], dfeat, grads)
+                if need_dX:
+                    dX = self._dX_from_dfeat(N, dfeat, st["feat"]["mask"])
+        return dX, dz

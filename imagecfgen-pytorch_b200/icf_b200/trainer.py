@@ -1,0 +1,241 @@
+"""Fused BiGAN train step (phases A-D of the reference loop) and the counterfactual pipeline.
+
+``BiGANTrainer.step`` reproduces one iteration of the hot loop of image_scms/mnist.py:220-248 (identical in
+audio_mnist.py:396-420, whalecalls.py:474-498, esrf_acoustic.py:353-377) with the minimal work that yields every
+reference output (4 F_E + 4 F_G + 12 F_D instead of 7/7/14):
+
+  A  E,G forward; D forward x2; BCE; D dgrad only; E,G full backward; Adam(E+G)
+  B  E forward (new weights); D forward; BCE; D backward; Adam(D)
+  C  G forward (new weights); D forward; BCE; D backward; Adam(D)
+  D  D forward x2 on the B/C activations (train mode: dropout + BatchNorm statistics); mean sigmoid scores
+
+Everything is launched on the current stream with no host synchronisation, so a whole step can be captured
+in a CUDA graph (``capture``).  Data parallelism: one process per GPU, the flat fp32 gradient buffers are
+all-reduced over NCCL in buckets overlapped with the remaining backward, one wave per optimiser step.
+"""
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .engine import Act, NetExec, draw_masks, dtype_code
+
+F32 = ops.F32
+
+
+class _FlatGroup:
+    """Parameters of one optimiser flattened into a single fp32 buffer (the nn.Parameters become views)."""
+
+    def __init__(self, named: List, device):
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]       # keep every tensor 16-byte aligned
+        self.offsets = [0]
+        for s in sizes:
+            self.offsets.append(self.offsets[-1] + s)
+        n = self.offsets[-1]
+        self.n = n
+        self.flat = torch.zeros(n, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=device)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=device)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=device)
+        self.grad_views = {}
+        with torch.no_grad():
+            for name, p, off in zip(self.names, self.params, self.offsets):
+                v = self.flat[off:off + p.numel()].view_as(p)
+                v.copy_(p.detach())
+                p.data = v
+                self.grad_views[name] = self.grad[off:off + p.numel()].view_as(p)
+
+    def segment(self, lo_name_idx, hi_name_idx):
+        return self.offsets[lo_name_idx], self.offsets[hi_name_idx]
+
+
+class BiGANTrainer:
+    def __init__(self, E, G, D, lr=1e-4, betas=None, eps=1e-8, dtype=None, process_group=None,
+                 overlap_allreduce=True):
+        self.E, self.G, self.D = E, G, D
+        if dtype is not None:
+            for m in (E, G, D):
+                m.set_compute_dtype(dtype)
+        self.exE, self.exG, self.exD = E.engine(), G.engine(), D.engine()
+        self.fam = self.exE.fam
+        self.device = self.exE.device
+        betas = betas if betas is not None else self.fam.adam_betas
+        # optimizer_E covers E.parameters() + G.parameters() (mnist.py:176-177)
+        eg_named = [("E." + n, p) for n, p in E.named_parameters()] + [("G." + n, p) for n, p in G.named_parameters()]
+        self.n_E = len(list(E.named_parameters()))
+        self.gEG = _FlatGroup(eg_named, self.device)
+        self.gD = _FlatGroup([("D." + n, p) for n, p in D.named_parameters()], self.device)
+        self.gradsE = {n[2:]: v for n, v in self.gEG.grad_views.items() if n.startswith("E.")}
+        self.gradsG = {n[2:]: v for n, v in self.gEG.grad_views.items() if n.startswith("G.")}
+        self.gradsD = {n[2:]: v for n, v in self.gD.grad_views.items()}
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        gs = 1.0 / self.world
+        self.stateEG = torch.tensor([0, lr, betas[0], betas[1], eps, gs, 0, 0], dtype=torch.float32, device=self.device)
+        self.stateD = self.stateEG.clone()
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.overlap = overlap_allreduce and self.world > 1
+        self.comm_stream = torch.cuda.Stream(device=self.device) if self.overlap else None
+        self.graph = None
+        self.static = None
+        for ex in (self.exE, self.exG, self.exD):
+            ex.repack(force=True)
+
+    # ---- collectives ------------------------------------------------------------------------------
+    def _allreduce(self, buf: torch.Tensor, side=False):
+        if self.world == 1:
+            return None
+        import torch.distributed as dist
+        if side and self.overlap:
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                dist.all_reduce(buf, group=self.pg)
+                done = torch.cuda.Event()
+                done.record()
+            return done
+        dist.all_reduce(buf, group=self.pg)
+        return None
+
+    def _adam(self, grp: _FlatGroup, state):
+        ops.adam_step(grp.flat.data_ptr(), grp.grad.data_ptr(), grp.exp_avg.data_ptr(), grp.exp_avg_sq.data_ptr(),
+                      grp.n, state.data_ptr())
+
+    # ---- one iteration ------------------------------------------------------------------------------
+    def step(self, images: torch.Tensor, c: Dict[str, torch.Tensor], z: Optional[torch.Tensor] = None,
+             masks6: Optional[List] = None, phase_a: bool = True, out: Optional[torch.Tensor] = None):
+        """images: (N,1,H,W)/(N,H,W) already scaled to [-1,1]; c: attribute dict already scaled; z: (N,latent,1,1)
+        or None (drawn on the device); masks6: six mask lists (A-valid, A-fake, B, C, D-fake, D-valid) or None.
+        Returns a device tensor [loss_EG, loss_D_valid, loss_D_fake, DG_mean, DE_mean] (accumulated into ``out``)."""
+        exE, exG, exD = self.exE, self.exG, self.exD
+        fam = self.fam
+        ops.require_cuda(images)
+        x = images.contiguous()
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        N = x.numel() // (exE.H * exE.W)
+        if z is None:
+            z = torch.randn(N, fam.latent, 1, 1, device=self.device)
+        z = z.contiguous().float()
+        xp, xc = x.data_ptr(), ops.code_of(x)
+        zp = z.data_ptr()
+        if masks6 is None:
+            masks6 = [None] * 6
+        if out is None:
+            out = torch.zeros(8, dtype=torch.float32, device=self.device)
+        dl = torch.empty((N, 1), dtype=torch.float32, device=self.device)
+        dl2 = torch.empty((N, 1), dtype=torch.float32, device=self.device)
+
+        with torch.cuda.device(self.device):
+            # ---- Phase A: encoder + generator update (mnist.py:224-230) --------------------------------
+            if phase_a:
+                ops.fill_f32(self.gEG.grad.data_ptr(), 0.0, self.gEG.n)
+                zE, stE = exE.encoder_forward(N, xp, xc, 1, c, save=True)
+                xG, stG = exG.generator_forward(N, zp, F32, fam.latent, c, save=True)
+                l1, sD1 = exD.discriminator_forward(N, xp, xc, 1, zE.ptr, zE.code, zE.pitch, c, masks=masks6[0])
+                l2, sD2 = exD.discriminator_forward(N, xG.ptr, xG.code, xG.pitch, zp, F32, fam.latent, c,
+                                                    masks=masks6[1])
+                ops.bce_logits(l1.ptr, F32, 1, N, 0.0, 0.5, ops.ptr(out, 0), dl.data_ptr(), F32, 1)
+                ops.bce_logits(l2.ptr, F32, 1, N, 1.0, 0.5, ops.ptr(out, 0), dl2.data_ptr(), F32, 1)
+                _, dzE = exD.discriminator_backward(sD1, Act(dl, 1), None, need_dz=True)
+                dXG, _ = exD.discriminator_backward(sD2, Act(dl2, 1), None, need_dX=True)
+                exE.encoder_backward(stE, Act(dzE, fam.latent), self.gradsE)
+                lo, hi = self.gEG.segment(0, self.n_E)
+                evE = self._allreduce(self.gEG.grad[lo:hi], side=True)
+                exG.generator_backward(stG, Act(dXG, 1), self.gradsG)
+                lo, hi = self.gEG.segment(self.n_E, len(self.gEG.params))
+                self._allreduce(self.gEG.grad[lo:hi])
+                if evE is not None:
+                    torch.cuda.current_stream().wait_event(evE)
+                self._adam(self.gEG, self.stateEG)
+                exE.repack(force=True)
+                exG.repack(force=True)
+                del stE, stG, sD1, sD2
+            # ---- Phase B: discriminator on real pairs (mnist.py:232-236) -------------------------------
+            ops.fill_f32(self.gD.grad.data_ptr(), 0.0, self.gD.n)
+            zE, _ = exE.encoder_forward(N, xp, xc, 1, c, save=False)
+            l, sD = exD.discriminator_forward(N, xp, xc, 1, zE.ptr, zE.code, zE.pitch, c, masks=masks6[2])
+            ops.bce_logits(l.ptr, F32, 1, N, 1.0, 1.0, ops.ptr(out, 1), dl.data_ptr(), F32, 1)
+            exD.discriminator_backward(sD, Act(dl, 1), self.gradsD)
+            self._allreduce(self.gD.grad)
+            self._adam(self.gD, self.stateD)
+            exD.repack(force=True)
+            # ---- Phase C: discriminator on generated pairs (mnist.py:237-241) --------------------------
+            ops.fill_f32(self.gD.grad.data_ptr(), 0.0, self.gD.n)
+            xG, _ = exG.generator_forward(N, zp, F32, fam.latent, c, save=False)
+            l, sD = exD.discriminator_forward(N, xG.ptr, xG.code, xG.pitch, zp, F32, fam.latent, c, masks=masks6[3])
+            ops.bce_logits(l.ptr, F32, 1, N, 0.0, 1.0, ops.ptr(out, 2), dl.data_ptr(), F32, 1)
+            exD.discriminator_backward(sD, Act(dl, 1), self.gradsD)
+            self._allreduce(self.gD.grad)
+            self._adam(self.gD, self.stateD)
+            exD.repack(force=True)
+            del sD
+            # ---- Phase D: scores (mnist.py:243-248); E(x), G(z) are those of phases B/C -----------------
+            l, _ = exD.discriminator_forward(N, xG.ptr, xG.code, xG.pitch, zp, F32, fam.latent, c, masks=masks6[4],
+                                             save=False)
+            ops.sigmoid_mean(l.ptr, F32, 1, N, ops.ptr(out, 3))
+            l, _ = exD.discriminator_forward(N, xp, xc, 1, zE.ptr, zE.code, zE.pitch, c, masks=masks6[5], save=False)
+            ops.sigmoid_mean(l.ptr, F32, 1, N, ops.ptr(out, 4))
+        return out
+
+    # ---- CUDA graph -------------------------------------------------------------------------------------
+    def capture(self, images, c, phase_a=True, warmup=2):
+        """Capture one step on static input buffers; ``replay(images, c)`` then copies inputs and launches it."""
+        self.static = {"x": images.clone(), "c": {k: v.clone() for k, v in c.items()},
+                       "out": torch.zeros(8, dtype=torch.float32, device=self.device)}
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.step(self.static["x"], self.static["c"], phase_a=phase_a, out=self.static["out"])
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step(self.static["x"], self.static["c"], phase_a=phase_a, out=self.static["out"])
+        self.graph = g
+        return g
+
+    def replay(self, images=None, c=None):
+        if images is not None:
+            self.static["x"].copy_(images, non_blocking=True)
+        if c is not None:
+            for k, v in c.items():
+                self.static["c"][k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.static["out"]
+
+    # ---- optimiser export (train() returns torch optimisers like the reference, mnist.py:299) -----------
+    def export_optimizers(self):
+        def make(params, grp: _FlatGroup, state):
+            opt = torch.optim.Adam(params, lr=self.lr, betas=self.betas, eps=self.eps)
+            steps = float(state[0].item())
+            for p, off in zip(grp.params, grp.offsets):
+                n = p.numel()
+                opt.state[p] = {"step": torch.tensor(steps), "exp_avg": grp.exp_avg[off:off + n].view_as(p).clone(),
+                                "exp_avg_sq": grp.exp_avg_sq[off:off + n].view_as(p).clone()}
+            return opt
+        optE = make(list(self.E.parameters()) + list(self.G.parameters()), self.gEG, self.stateEG)
+        optD = make(list(self.D.parameters()), self.gD, self.stateD)
+        return optD, optE
+
+
+def counterfactual(E, G, x: torch.Tensor, c: Dict[str, torch.Tensor], c_cf: Dict[str, torch.Tensor],
+                   out: Optional[torch.Tensor] = None):
+    """G(E(x, c), c_cf) without gradients (mnist_gan_counterfactuals.py:71) as one device-resident pipeline:
+    the latent code stays in the engine's buffer (never converted or copied) between encode and decode."""
+    exE, exG = E.engine(), G.engine()
+    ops.require_cuda(x)
+    xx = x.contiguous()
+    if xx.dtype not in (torch.float32, torch.bfloat16):
+        xx = xx.float()
+    N = xx.numel() // (exE.H * exE.W)
+    with torch.no_grad(), torch.cuda.device(exE.device):
+        zE, _ = exE.encoder_forward(N, xx.data_ptr(), ops.code_of(xx), 1, c, save=False)
+        img, _ = exG.generator_forward(N, zE.ptr, zE.code, zE.pitch, c_cf, save=False)
+        if out is None:
+            out = torch.empty((N, 1, exE.H, exE.W), dtype=torch.float32, device=exE.device)
+        ops.cast(img.ptr, img.code, out.data_ptr(), ops.code_of(out), out.numel())
+    return out

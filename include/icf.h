@@ -1,0 +1,234 @@
+/*
+ * icf.h — C-ABI of the B200-native conditional-BiGAN hot path (libicf_b200.so).
+ *
+ * The reference (wtaylor17/ImageCFGen-Pytorch) has no FFI: its hot path is the stock torch.nn layers
+ * called from image_scms/{mnist,audio_mnist,whalecalls,esrf_acoustic}.py.  Each entry point below
+ * replaces the torch operator(s) named in its comment (reference file:line); the Python host side in
+ * imagecfgen-pytorch_b200/ binds them with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller (PyTorch's
+ *    caching allocator); the library never allocates or frees tensor memory and never synchronises.
+ *  - every launch goes to the `stream` argument (a cudaStream_t passed as void*).
+ *  - return 0 on success; non-zero -> icf_last_error() (thread-local) describes the failure. Invalid
+ *    shapes / alignments are reported, never abort()ed. Asynchronous CUDA faults surface at the caller's
+ *    next synchronisation, as with torch.
+ *  - activations are NHWC ("pixel-major"): tensor[n][y][x][pitch], `pitch` >= channels, both multiples
+ *    of 8 for bf16 tensor-core operands. At the module boundary C==1 or H==W==1, so NCHW == NHWC.
+ *  - re-entrant: may be called from the Python thread and from torch's autograd worker thread.
+ */
+#ifndef ICF_H_
+#define ICF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICF_VERSION 1
+
+enum { ICF_F32 = 0, ICF_BF16 = 1 };
+enum { ICF_ACT_NONE = 0, ICF_ACT_LRELU = 1, ICF_ACT_TANH = 2 };
+enum { ICF_FORM_GATHER = 0,    /* src = dst*stride - pad + tap           (Conv2d fprop, ConvT dgrad) */
+       ICF_FORM_TRANSPOSED = 1 /* src = (dst + pad - tap)/stride, exact  (ConvT fprop, Conv2d dgrad) */ };
+
+const char* icf_last_error(void);
+int icf_version(void);
+/* 1 when the tcgen05/TMEM implicit-GEMM path is compiled in and allowed (env ICF_DISABLE_TC unset). */
+int icf_tc_enabled(void);
+void icf_set_tc_enabled(int on);
+
+/* ------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution, forward and data-gradient.
+ * Replaces aten::convolution / transposed convolution of nn.Conv2d, nn.ConvTranspose2d, nn.Linear
+ * (image_scms/mnist.py:31-39,64-72,100-135; audio_mnist.py:187-197,226-242,273-302) and the dgrad half
+ * of aten::convolution_backward, fused with bias + LeakyReLU/Tanh (+ Dropout2d mask, + BatchNorm
+ * statistics of the result).
+ *   dst[n,p,q,k] = mask[n,k] * act( bias[k] + sum_{r,s,c} src[n, y(p,r), x(q,s), c] * w[k][r*S+s][c] )
+ * bf16: tcgen05.mma with TMEM accumulators, operands staged by TMA; f32: SIMT FMA.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct icf_conv_args {
+  int32_t dtype;                 /* ICF_F32 | ICF_BF16: element type of src, w and (unless out_f32) dst */
+  int32_t form;                  /* ICF_FORM_* */
+  int32_t N;
+  int32_t H, W, C, in_pitch;     /* src [N][H][W][in_pitch], C channels reduced over */
+  int32_t P, Q, K, out_pitch;    /* dst [N][P][Q][out_pitch], K channels produced */
+  int32_t R, S, stride, pad;
+  int32_t w_rows;                /* rows physically present in w (>= K; extra rows must be zero) */
+  int32_t w_pitch;               /* channels physically present per (row, tap) of w (>= C, zero padded) */
+  int32_t act;                   /* ICF_ACT_* */
+  float slope;                   /* LeakyReLU negative slope */
+  int32_t out_f32;               /* 1: dst elements are float even when dtype == ICF_BF16 */
+  int32_t mask_pitch;            /* row pitch of out_mask */
+  int32_t accumulate;            /* 1: dst += result (f32 dst only; used by split dgrad) */
+  const void* src;
+  const void* w;                 /* packed [w_rows][R*S][w_pitch], channels contiguous */
+  const float* bias;             /* [K] or NULL */
+  void* dst;
+  const float* out_mask;         /* [N][mask_pitch] Dropout2d mask incl. 1/(1-p) scale, or NULL */
+  float* stats;                  /* [2][K]: += sum, += sum of squares of dst values (BatchNorm), or NULL */
+} icf_conv_args;
+int icf_conv_forward(const icf_conv_args* a, void* stream);
+
+/* Weight gradient (the wgrad half of aten::convolution_backward), fp32 accumulation, split over pixels:
+ *   dw[a][r*S+s][b] += sum_{n,p,q} small[n,p,q,a] * big[n, p*stride-pad+r, q*stride-pad+s, b]
+ * Conv2d: small = dY, big = X.  ConvTranspose2d: small = X, big = dY. */
+typedef struct icf_wgrad_args {
+  int32_t dtype;
+  int32_t N;
+  int32_t P, Q, A, a_pitch;
+  int32_t H, W, B, b_pitch;
+  int32_t R, S, stride, pad;
+  const void* small_t;
+  const void* big_t;
+  float* dw;                     /* [A][R*S][B] fp32, caller zeroes */
+} icf_wgrad_args;
+int icf_conv_wgrad(const icf_wgrad_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weight (re)packing between the checkpoint layout (fp32 OIHW / IOHW / [out,in], App. A.5 of SURVEY.md)
+ * and the K-major operand layout the conv kernels read.  Generic 3-index permutation:
+ *   pack:    dst[i0][i1][i2] (dense, i2 padded to d2_pad, rows padded to rows_pad with zeros)
+ *              = src[i0*s0 + i1*s1 + i2*s2]
+ *   unpack:  dst[i0*s0 + i1*s1 + i2*s2] (=|+=) src[i0][i1][i2]        (fp32 -> fp32, for gradients)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct icf_perm {
+  int64_t d0, d1, d2;            /* logical extents */
+  int64_t s0, s1, s2;            /* element strides in the checkpoint-layout tensor */
+  int64_t d2_pad;                /* physical extent of i2 in the packed tensor (>= d2) */
+  int64_t d0_pad;                /* physical extent of i0 in the packed tensor (>= d0) */
+} icf_perm;
+int icf_pack(const float* src, void* dst, int32_t dst_dtype, const icf_perm* p, void* stream);
+int icf_unpack(const float* src_packed, float* dst, const icf_perm* p, int32_t atomic_add, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attribute / latent feature assembly (mnist.py:47-55,77-85; audio_mnist.py:204-210,250-256).
+ * ------------------------------------------------------------------------------------------------ */
+#define ICF_MAX_PLANES 8
+/* first-max argmax over rows of a one-hot / score matrix -> int32 (torch.argmax semantics) */
+int icf_argmax_rows(const void* x, int32_t x_dtype /*0 f32,1 bf16,2 i32,3 i64*/, int32_t n, int32_t k,
+                    int32_t* out, void* stream);
+
+typedef struct icf_imgfeat_args {
+  int32_t dtype;                 /* dtype of feat */
+  int32_t N, H, W;
+  int32_t feat_pitch;            /* channels physically present in feat (multiple of 8) */
+  int32_t x_dtype;               /* dtype of x: ICF_F32 or ICF_BF16 */
+  int32_t x_pitch;               /* elements between consecutive pixels of x (1 for a plain image) */
+  int32_t n_emb, n_cont;
+  int32_t mask_pitch;
+  const void* x;                 /* [N][H][W][x_pitch], channel 0 is the image */
+  const float* emb_table[ICF_MAX_PLANES];   /* [K_i][256] */
+  const int32_t* emb_index[ICF_MAX_PLANES]; /* [N] */
+  const float* cont[ICF_MAX_PLANES];        /* [N] constant-plane values */
+  const float* mask;             /* [N][mask_pitch] Dropout2d mask on the feature stack, or NULL */
+  void* feat;                    /* [N][H][W][feat_pitch]: ch0 image, then embedding planes, then constants */
+  /* backward only */
+  const void* dfeat;             /* [N][H][W][feat_pitch] gradient w.r.t. feat */
+  float* demb_table[ICF_MAX_PLANES];        /* [K_i][256] += */
+} icf_imgfeat_args;
+int icf_image_features_fwd(const icf_imgfeat_args* a, void* stream);
+int icf_image_features_bwd(const icf_imgfeat_args* a, void* stream);
+
+typedef struct icf_latfeat_args {
+  int32_t dtype;                 /* dtype of feat */
+  int32_t N, latent;
+  int32_t feat_pitch;            /* >= latent + 256*n_emb + n_cont, multiple of 8 */
+  int32_t z_dtype, z_pitch;
+  int32_t n_emb, n_cont;
+  int32_t emb_k[ICF_MAX_PLANES];
+  const void* z;                 /* [N][z_pitch] */
+  const float* emb_table[ICF_MAX_PLANES];   /* [K_i][256] */
+  const float* onehot[ICF_MAX_PLANES];      /* [N][K_i] dense (soft one-hots allowed) */
+  const float* cont[ICF_MAX_PLANES];        /* [N] */
+  void* feat;                    /* [N][feat_pitch] */
+  /* backward only (any output may be NULL) */
+  const void* dfeat;             /* [N][feat_pitch] */
+  float* dz;                     /* [N][latent] = */
+  float* demb_table[ICF_MAX_PLANES];        /* [K_i][256] += */
+  float* donehot[ICF_MAX_PLANES];           /* [N][K_i] = */
+  float* dcont[ICF_MAX_PLANES];             /* [N] = */
+} icf_latfeat_args;
+int icf_latent_features_fwd(const icf_latfeat_args* a, void* stream);
+int icf_latent_features_bwd(const icf_latfeat_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm2d in training mode (mnist.py:111,114,118,122) split around the convolutions:
+ *  - the producing conv accumulates stats[2][C];
+ *  - icf_bn_finalize turns them into scale/shift, saves mean/invstd, updates the running statistics
+ *    (momentum 0.1, unbiased running_var, num_batches_tracked += 1), and re-zeroes `stats`;
+ *  - icf_scale_shift_mask applies u = mask[n,c] * (scale[c]*y + shift[c]) (BatchNorm + Dropout2d),
+ *    also used alone for a bare Dropout2d or a dtype cast.
+ * ------------------------------------------------------------------------------------------------ */
+int icf_bn_finalize(float* stats, int32_t C, double count, const float* gamma, const float* beta,
+                    float eps, float momentum, float* running_mean, float* running_var,
+                    int64_t* num_batches_tracked, float* scale, float* shift, float* save_mean,
+                    float* save_invstd, void* stream);
+int icf_scale_shift_mask(const void* y, int32_t y_dtype, int32_t y_pitch, void* u, int32_t u_dtype,
+                         int32_t u_pitch, int64_t pixels, int32_t pixels_per_sample, int32_t C,
+                         const float* scale, const float* shift, const float* mask, int32_t mask_pitch,
+                         void* stream);
+/* sums[0][c] = sum du, sums[1][c] = sum du * xhat, du = dU*mask, xhat = (y-mean)*invstd  (+=) */
+int icf_bn_bwd_reduce(const void* dU, int32_t d_dtype, int32_t d_pitch, const void* y, int32_t y_dtype,
+                      int32_t y_pitch, int64_t pixels, int32_t pixels_per_sample, int32_t C,
+                      const float* mask, int32_t mask_pitch, const float* save_mean,
+                      const float* save_invstd, float* sums, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward of the fused conv epilogue (aten::leaky_relu_backward / tanh_backward / dropout backward /
+ * native_batch_norm_backward / bias gradient in one pass):
+ *   g      = dOut[n,pix,c]                                   (gradient w.r.t. what the consumer read)
+ *   if bn: g = gamma*invstd*( g*bn_mask - sums0/M - xhat*sums1/M ),  dgamma += sums1, dbeta += sums0 (once)
+ *   dPre   = g * out_mask[n,c] * act'(y)                     (act' from the saved output y)
+ *   dbias[c] += sum dPre
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct icf_actbwd_args {
+  int32_t d_dtype, d_pitch;      /* dOut */
+  int32_t y_dtype, y_pitch;      /* saved layer output y */
+  int32_t p_dtype, p_pitch;      /* dPre (written) */
+  int64_t pixels;                /* N*P*Q */
+  int32_t pixels_per_sample;
+  int32_t C;
+  int32_t act; float slope;
+  int32_t mask_pitch, bn_mask_pitch;
+  const void* dOut; const void* y; void* dPre;
+  const float* out_mask;         /* Dropout2d mask applied in the forward epilogue, or NULL */
+  float* dbias;                  /* [C] += , or NULL */
+  int32_t bias_mod;              /* dbias index = c % bias_mod (0: = c) */
+  /* BatchNorm that followed this layer's output (NULL bn_sums: none) */
+  const float* bn_sums;          /* [2][C] from icf_bn_bwd_reduce */
+  const float* bn_mask;          /* Dropout2d mask applied after the BatchNorm, or NULL */
+  const float* bn_gamma; const float* bn_mean; const float* bn_invstd;
+  float* bn_dgamma; float* bn_dbeta;   /* [C] += */
+} icf_actbwd_args;
+int icf_act_backward(const icf_actbwd_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * nn.BCEWithLogitsLoss (mnist.py:181,228,234,239) forward + backward in one kernel:
+ *   loss_out[0] += weight * mean_n( max(l,0) - l*t + log1p(exp(-|l|)) )
+ *   dlogits[n]   = weight * (sigmoid(l) - t) / N
+ * and the phase-D score (mnist.py:245-248): score_out[0] += mean_n sigmoid(l).
+ * ------------------------------------------------------------------------------------------------ */
+int icf_bce_logits(const void* logits, int32_t l_dtype, int32_t l_pitch, int32_t n, float target,
+                   float weight, float* loss_out, void* dlogits, int32_t d_dtype, int32_t d_pitch,
+                   void* stream);
+int icf_sigmoid_mean(const void* logits, int32_t l_dtype, int32_t l_pitch, int32_t n, float* score_out,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * torch.optim.Adam (mnist.py:176-179; eps 1e-8, no weight decay) over one flat fp32 buffer.
+ * `state` = {step, lr, beta1, beta2, eps, grad_scale} in device memory so a captured CUDA graph can
+ * be replayed: the kernel itself advances `step`.
+ * ------------------------------------------------------------------------------------------------ */
+int icf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  float* state /*[8]*/, void* stream);
+
+/* small utilities */
+int icf_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
+int icf_fill_f32(float* dst, float value, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICF_H_ */
