@@ -5,6 +5,7 @@ be captured into a CUDA graph.  torch is used for device memory and streams only
 stands in for a kernel here, and a missing libicf_b200.so raises (icf_b200.lib.load).
 """
 import ctypes as C
+import functools
 
 import torch
 
@@ -47,6 +48,33 @@ def ptr(t, offset_elems: int = 0):
     return t.data_ptr() + offset_elems * t.element_size()
 
 
+LAUNCHES = 0          # C-ABI launch calls made so far (bench.py reports the per-step count)
+PROFILE = None        # set to a list to record (name, start_event, end_event, flops, bytes) per launch
+
+
+def _launch(name, fn, *args, flops=0.0, nbytes=0.0):
+    global LAUNCHES
+    LAUNCHES += 1
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st = fn(*args, stream())
+        e1.record()
+        PROFILE.append((name, e0, e1, flops, nbytes))
+    else:
+        st = fn(*args, stream())
+    _l.check(st, name)
+
+
+@functools.lru_cache(maxsize=None)
+def valid_taps(form, H, P, R, stride, pad):
+    """Sum over output positions of the kernel taps that land inside the un-padded input."""
+    if form == GATHER:
+        return sum(1 for p in range(P) for r in range(R) if 0 <= p * stride - pad + r < H)
+    return sum(1 for p in range(P) for r in range(R)
+               if (p + pad - r) >= 0 and (p + pad - r) % stride == 0 and (p + pad - r) // stride < H)
+
+
 def conv_forward(dtype, form, N, H, W, Cc, in_pitch, P, Q, K, out_pitch, R, S, stride, pad,
                  src, w, w_rows, w_pitch, dst, bias=None, act="none", slope=0.0, out_f32=False,
                  mask=None, mask_pitch=0, stats=None, accumulate=False):
@@ -54,14 +82,22 @@ def conv_forward(dtype, form, N, H, W, Cc, in_pitch, P, Q, K, out_pitch, R, S, s
     a = _l.ConvArgs(dtype, form, N, H, W, Cc, in_pitch, P, Q, K, out_pitch, R, S, stride, pad,
                     w_rows, w_pitch, ACT[act], slope, 1 if out_f32 else 0, mask_pitch,
                     1 if accumulate else 0, src, w, bias, dst, mask, stats)
-    L = _l.load()
-    _l.check(L.icf_conv_forward(C.byref(a), stream()), "icf_conv_forward")
+    fl = nb = 0.0
+    if PROFILE is not None:
+        es = 4 if dtype == F32 else 2
+        fl = 2.0 * N * Cc * K * valid_taps(form, H, P, R, stride, pad) * valid_taps(form, W, Q, S, stride, pad)
+        nb = float(es) * (N * (H * W * Cc + P * Q * K) + K * Cc * R * S)
+    _launch("icf_conv_forward", _l.load().icf_conv_forward, C.byref(a), flops=fl, nbytes=nb)
 
 
 def conv_wgrad(dtype, N, P, Q, A, a_pitch, H, W, B, b_pitch, R, S, stride, pad, small, big, dw):
     a = _l.WgradArgs(dtype, N, P, Q, A, a_pitch, H, W, B, b_pitch, R, S, stride, pad, small, big, dw)
-    L = _l.load()
-    _l.check(L.icf_conv_wgrad(C.byref(a), stream()), "icf_conv_wgrad")
+    fl = nb = 0.0
+    if PROFILE is not None:
+        es = 4 if dtype == F32 else 2
+        fl = 2.0 * N * A * B * valid_taps(GATHER, H, P, R, stride, pad) * valid_taps(GATHER, W, Q, S, stride, pad)
+        nb = float(es) * N * (H * W * B + P * Q * A) + 4.0 * A * B * R * S
+    _launch("icf_conv_wgrad", _l.load().icf_conv_wgrad, C.byref(a), flops=fl, nbytes=nb)
 
 
 def make_perm(d0, d1, d2, s0, s1, s2, d2_pad=None, d0_pad=None):
@@ -69,13 +105,11 @@ def make_perm(d0, d1, d2, s0, s1, s2, d2_pad=None, d0_pad=None):
 
 
 def pack(src, dst, dst_dtype, perm):
-    L = _l.load()
-    _l.check(L.icf_pack(src, dst, dst_dtype, C.byref(perm), stream()), "icf_pack")
+    _launch("icf_pack", _l.load().icf_pack, src, dst, dst_dtype, C.byref(perm))
 
 
 def unpack(src_packed, dst, perm, atomic_add=False):
-    L = _l.load()
-    _l.check(L.icf_unpack(src_packed, dst, C.byref(perm), 1 if atomic_add else 0, stream()), "icf_unpack")
+    _launch("icf_unpack", _l.load().icf_unpack, src_packed, dst, C.byref(perm), 1 if atomic_add else 0)
 
 
 _ARGMAX_DT = {torch.float32: 0, torch.bfloat16: 1, torch.int32: 2, torch.int64: 3}
@@ -89,9 +123,7 @@ def argmax_rows(x: torch.Tensor) -> torch.Tensor:
     x = x.contiguous()
     n, k = x.shape
     out = torch.empty(n, dtype=torch.int32, device=x.device)
-    L = _l.load()
-    _l.check(L.icf_argmax_rows(x.data_ptr(), _ARGMAX_DT[x.dtype], n, k, out.data_ptr(), stream()),
-             "icf_argmax_rows")
+    _launch("icf_argmax_rows", _l.load().icf_argmax_rows, x.data_ptr(), _ARGMAX_DT[x.dtype], n, k, out.data_ptr())
     return out
 
 
@@ -113,11 +145,10 @@ def image_features(dtype, N, H, W, feat_pitch, x, x_dtype, x_pitch, tables, indi
     a.cont = _vp_array(conts)
     a.mask, a.feat, a.dfeat = mask, feat, dfeat
     a.demb_table = _vp_array(dtables or [])
-    L = _l.load()
     if backward:
-        _l.check(L.icf_image_features_bwd(C.byref(a), stream()), "icf_image_features_bwd")
+        _launch("icf_image_features_bwd", _l.load().icf_image_features_bwd, C.byref(a))
     else:
-        _l.check(L.icf_image_features_fwd(C.byref(a), stream()), "icf_image_features_fwd")
+        _launch("icf_image_features_fwd", _l.load().icf_image_features_fwd, C.byref(a))
 
 
 def latent_features(dtype, N, latent, feat_pitch, z, z_dtype, z_pitch, emb_k, tables, onehots, conts, feat,
@@ -135,32 +166,28 @@ def latent_features(dtype, N, latent, feat_pitch, z, z_dtype, z_pitch, emb_k, ta
     a.demb_table = _vp_array(dtables or [])
     a.donehot = _vp_array(donehots or [])
     a.dcont = _vp_array(dconts or [])
-    L = _l.load()
     if backward:
-        _l.check(L.icf_latent_features_bwd(C.byref(a), stream()), "icf_latent_features_bwd")
+        _launch("icf_latent_features_bwd", _l.load().icf_latent_features_bwd, C.byref(a))
     else:
-        _l.check(L.icf_latent_features_fwd(C.byref(a), stream()), "icf_latent_features_fwd")
+        _launch("icf_latent_features_fwd", _l.load().icf_latent_features_fwd, C.byref(a))
 
 
 def bn_finalize(stats, Cc, count, gamma, beta, eps, momentum, rmean, rvar, nbt, scale, shift, save_mean,
                 save_invstd):
-    L = _l.load()
-    _l.check(L.icf_bn_finalize(stats, Cc, float(count), gamma, beta, eps, momentum, rmean, rvar, nbt, scale,
-                               shift, save_mean, save_invstd, stream()), "icf_bn_finalize")
+    _launch("icf_bn_finalize", _l.load().icf_bn_finalize, stats, Cc, float(count), gamma, beta, eps, momentum, rmean, rvar, nbt, scale,
+                               shift, save_mean, save_invstd)
 
 
 def scale_shift_mask(y, y_dtype, y_pitch, u, u_dtype, u_pitch, pixels, pixels_per_sample, Cc, scale=None,
                      shift=None, mask=None, mask_pitch=0):
-    L = _l.load()
-    _l.check(L.icf_scale_shift_mask(y, y_dtype, y_pitch, u, u_dtype, u_pitch, pixels, pixels_per_sample, Cc,
-                                    scale, shift, mask, mask_pitch, stream()), "icf_scale_shift_mask")
+    _launch("icf_scale_shift_mask", _l.load().icf_scale_shift_mask, y, y_dtype, y_pitch, u, u_dtype, u_pitch, pixels, pixels_per_sample, Cc,
+                                    scale, shift, mask, mask_pitch)
 
 
 def bn_bwd_reduce(dU, d_dtype, d_pitch, y, y_dtype, y_pitch, pixels, pps, Cc, mask, mask_pitch, mean, invstd,
                   sums):
-    L = _l.load()
-    _l.check(L.icf_bn_bwd_reduce(dU, d_dtype, d_pitch, y, y_dtype, y_pitch, pixels, pps, Cc, mask, mask_pitch,
-                                 mean, invstd, sums, stream()), "icf_bn_bwd_reduce")
+    _launch("icf_bn_bwd_reduce", _l.load().icf_bn_bwd_reduce, dU, d_dtype, d_pitch, y, y_dtype, y_pitch, pixels, pps, Cc, mask, mask_pitch,
+                                 mean, invstd, sums)
 
 
 def act_backward(dOut, d_dtype, d_pitch, y, y_dtype, y_pitch, dPre, p_dtype, p_pitch, pixels, pps, Cc, act,
@@ -169,31 +196,24 @@ def act_backward(dOut, d_dtype, d_pitch, y, y_dtype, y_pitch, dPre, p_dtype, p_p
     a = _l.ActBwdArgs(d_dtype, d_pitch, y_dtype, y_pitch, p_dtype, p_pitch, pixels, pps, Cc, ACT[act], slope,
                       mask_pitch, bn_mask_pitch, dOut, y, dPre, out_mask, dbias, 0, bn_sums, bn_mask, bn_gamma,
                       bn_mean, bn_invstd, bn_dgamma, bn_dbeta)
-    L = _l.load()
-    _l.check(L.icf_act_backward(C.byref(a), stream()), "icf_act_backward")
+    _launch("icf_act_backward", _l.load().icf_act_backward, C.byref(a))
 
 
 def bce_logits(logits, l_dtype, l_pitch, n, target, weight, loss_out, dlogits, d_dtype, d_pitch):
-    L = _l.load()
-    _l.check(L.icf_bce_logits(logits, l_dtype, l_pitch, n, target, weight, loss_out, dlogits, d_dtype, d_pitch,
-                              stream()), "icf_bce_logits")
+    _launch("icf_bce_logits", _l.load().icf_bce_logits, logits, l_dtype, l_pitch, n, target, weight, loss_out, dlogits, d_dtype, d_pitch)
 
 
 def sigmoid_mean(logits, l_dtype, l_pitch, n, score_out):
-    L = _l.load()
-    _l.check(L.icf_sigmoid_mean(logits, l_dtype, l_pitch, n, score_out, stream()), "icf_sigmoid_mean")
+    _launch("icf_sigmoid_mean", _l.load().icf_sigmoid_mean, logits, l_dtype, l_pitch, n, score_out)
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, n, state):
-    L = _l.load()
-    _l.check(L.icf_adam_step(param, grad, exp_avg, exp_avg_sq, n, state, stream()), "icf_adam_step")
+    _launch("icf_adam_step", _l.load().icf_adam_step, param, grad, exp_avg, exp_avg_sq, n, state)
 
 
 def cast(src, src_dtype, dst, dst_dtype, n):
-    L = _l.load()
-    _l.check(L.icf_cast(src, src_dtype, dst, dst_dtype, n, stream()), "icf_cast")
+    _launch("icf_cast", _l.load().icf_cast, src, src_dtype, dst, dst_dtype, n)
 
 
 def fill_f32(dst, value, n):
-    L = _l.load()
-    _l.check(L.icf_fill_f32(dst, value, n, stream()), "icf_fill_f32")
+    _launch("icf_fill_f32", _l.load().icf_fill_f32, dst, value, n)

@@ -1,0 +1,153 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/icf.h declares, the drop-in modules
+keep the reference's state_dict layout, host logic (batching, mask order, FLOP accounting, flat parameter
+groups, 2-rank gloo gradient averaging) — no kernel is launched here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    from icf_b200 import lib
+    hdr = open(os.path.join(ROOT, "include", "icf.h")).read()
+    declared = set(re.findall(r"\b(icf_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"icf_conv_args", "icf_wgrad_args"}
+    assert os.path.exists(lib.LIB_PATH), "build with python imagecfgen-pytorch_b200/build.py"
+    h = ctypes.CDLL(lib.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(h, s)]
+    assert not missing, missing
+    assert set(lib.EXPORTED_SYMBOLS) == declared
+    assert lib.load().icf_version() == 1
+
+
+def test_struct_layouts_match_header_sizes():
+    """ctypes mirrors of the argument structs must have the C sizes (checked against a tiny gcc program)."""
+    from icf_b200 import lib
+    src = r'''
+#include <stdio.h>
+#include "icf.h"
+int main(){printf("%zu %zu %zu %zu %zu %zu\n", sizeof(icf_conv_args), sizeof(icf_wgrad_args), sizeof(icf_perm),
+ sizeof(icf_imgfeat_args), sizeof(icf_latfeat_args), sizeof(icf_actbwd_args));return 0;}'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = list(map(int, subprocess.check_output([exe]).split()))
+    mine = [ctypes.sizeof(t) for t in (lib.ConvArgs, lib.WgradArgs, lib.Perm, lib.ImgFeatArgs, lib.LatFeatArgs,
+                                       lib.ActBwdArgs)]
+    assert mine == sizes, (mine, sizes)
+
+
+@pytest.mark.parametrize("fam", ["mnist", "audio_mnist", "whalecalls", "esrf_acoustic"])
+def test_state_dict_layout_matches_reference_tables(fam):
+    import importlib
+    from oracle.arch import param_shapes
+    m = importlib.import_module(f"image_scms.{fam}")
+    with torch.device("meta"):
+        nets = {"E": m.Encoder(), "G": m.Generator(), "D": m.Discriminator()}
+    for k, net in nets.items():
+        sd = net.state_dict()
+        want = param_shapes(fam, k)
+        got = [(n, tuple(v.shape)) for n, v in sd.items() if not n.endswith("num_batches_tracked")]
+        assert got == [(n, tuple(s)) for n, s in want], (fam, k)
+        assert type(net).__module__ == f"image_scms.{fam}"
+
+
+def test_default_init_and_init_weights():
+    from image_scms import mnist
+    from image_scms.training_utils import init_weights
+    torch.manual_seed(0)
+    D = mnist.Discriminator()
+    w = D.dxz._modules["1"].weight
+    bound = 1 / (1024 ** 0.5)
+    assert float(w.abs().max()) <= bound and float(w.std()) > 0.5 * bound / 3 ** 0.5
+    emb0 = D.digit_embedding._modules["0"].weight.clone()
+    bn_w = D.dx._modules["4"].weight.clone()
+    D.apply(init_weights)
+    assert abs(float(D.dxz._modules["1"].weight.std()) - 0.01) < 1e-3
+    assert float(D.dxz._modules["1"].bias.abs().max()) == 0.0
+    assert torch.equal(emb0, D.digit_embedding._modules["0"].weight)      # Embedding / BN keep torch defaults
+    assert torch.equal(bn_w, D.dx._modules["4"].weight)
+
+
+def test_cpu_tensors_are_refused():
+    from image_scms import mnist
+    E = mnist.Encoder()
+    c = {"digit": torch.eye(10)[:2], "thickness": torch.zeros(2, 1), "intensity": torch.zeros(2, 1),
+         "slant": torch.zeros(2, 1)}
+    with pytest.raises(RuntimeError, match="no CPU"):
+        E(torch.zeros(2, 1, 28, 28), c)
+
+
+def test_batchify_and_mask_sites():
+    from image_scms.training_utils import batchify, batchify_dict
+    x, y = torch.arange(10), torch.arange(10) * 2
+    got = list(batchify(x, y, batch_size=4))
+    assert [len(b[0]) for b in got] == [4, 4, 2] and torch.equal(got[2][1], torch.tensor([16, 18]))
+    gd = list(batchify_dict({"a": x, "b": y}, batch_size=3))
+    assert [len(b["a"]) for b in gd] == [3, 3, 3, 1]
+    from icf_b200.arch import FAMILIES
+    from icf_b200.engine import mask_sites
+    sites = [(p, c) for (_, _, _, p, c) in mask_sites(FAMILIES["mnist"])]
+    assert sites == [(0.2, 5), (0.2, 32), (0.5, 64), (0.5, 128), (0.5, 256), (0.2, 512), (0.5, 512), (0.2, 1024),
+                     (0.2, 1024), (0.2, 1024)]
+    from oracle.bigan_ref import dropout_sites
+    assert sites == dropout_sites("mnist")
+    assert mask_sites(FAMILIES["audio_mnist"]) == []
+
+
+def test_flop_accounting_matches_survey():
+    """per-image forward FLOPs (valid taps)."""
+    from icf_b200.arch import FAMILIES, forward_flops_per_image
+    f = forward_flops_per_image(FAMILIES["mnist"])
+    assert abs(f["E"] / 1e6 - 22.96) < 0.01 and abs(f["G"] / 1e6 - 75.71) < 0.01 and abs(f["D"] / 1e6 - 46.36) < 0.01
+    f = forward_flops_per_image(FAMILIES["audio_mnist"])
+    assert abs(f["E"] / 1e6 - 1293.2) < 0.5 and abs(f["G"] / 1e6 - 1534.3) < 0.5 and abs(f["D"] / 1e6 - 1298.5) < 0.5
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from icf_b200.trainer import _FlatGroup
+from image_scms import mnist
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+torch.manual_seed(0)
+E, G = mnist.Encoder(), mnist.Generator()
+named = [("E." + n, p) for n, p in E.named_parameters()] + [("G." + n, p) for n, p in G.named_parameters()]
+grp = _FlatGroup(named, torch.device("cpu"))
+n_E = len(list(E.named_parameters()))
+assert all(p.data_ptr() >= grp.flat.data_ptr() for p in grp.params)          # parameters became views
+for name, v in grp.grad_views.items():
+    v.fill_(float(rank + 1))
+# two buckets (E first, then G), as BiGANTrainer.step launches them
+for lo_i, hi_i in ((0, n_E), (n_E, len(grp.params))):
+    lo, hi = grp.segment(lo_i, hi_i)
+    dist.all_reduce(grp.grad[lo:hi])
+avg = grp.grad / world
+want = sum(range(1, world + 1)) / world
+ok = all(bool((avg[o:o + p.numel()] == want).all()) for p, o in zip(grp.params, grp.offsets))
+dist.barrier()
+print("OK" if ok else "BAD", flush=True)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_gradient_buckets(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), os.path.join(ROOT, "imagecfgen-pytorch_b200")],
+                              env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("OK" in o for o in outs), outs
