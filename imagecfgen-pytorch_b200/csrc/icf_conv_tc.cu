@@ -1,4 +1,498 @@
-// tcgen05 / TMEM / TMA implicit-GEMM path (placeholder until the kernel lands): -1 = "not handled".
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+//   D[m][k] = epi( sum_{tap, c} A[pix(m, tap)][c] * Wp[k][tap][c] )        m = output pixel, k = output channel
+//
+// One CTA computes a 128 x TILE_N tile of D.  The 128 rows are a BOX (tn images x ti rows x tj columns) of the
+// output index space of one "class"; for a fixed filter tap the source pixels of such a box are again a box of
+// the NHWC activation tensor, so a single 4-D TMA tiled load (traversal stride = conv stride, out-of-bounds =
+// zero = padding) brings the 128 x 64-channel A operand of that tap into shared memory in the 128B-swizzled
+// K-major layout tcgen05.mma reads.  The transposed form (ConvTranspose2d forward / Conv2d dgrad) is split into
+// stride^2 output-parity classes, each a unit-stride gather over the taps of its parity — no zero insertion.
+// Taps whose source box lies entirely in the padding are skipped by producer and MMA issuer alike.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..5 = epilogue (TMEM -> registers -> bias/activation/Dropout2d mask -> global), one D row per thread.
 #include "icf_common.cuh"
-int icf_tc_conv_forward(const icf_conv_args*, cudaStream_t) { return -1; }
+
+#include <cuda.h>
+
+namespace {
+
+constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
+constexpr int MAX_CLASSES = 16, MAX_TAPS = 25;
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 26;   // a wedged pipeline traps instead of hanging the GPU
+
+struct TapTable {
+  int16_t ntaps[MAX_CLASSES];
+  int8_t tap[MAX_CLASSES][MAX_TAPS];   // index r*S+s into the packed weights
+  int8_t dy[MAX_CLASSES][MAX_TAPS];    // source row    = i*sstep + dy
+  int8_t dx[MAX_CLASSES][MAX_TAPS];    // source column = j*sstep + dx
+};
+
+struct TcParams {
+  int N, H, W, C;
+  int P, Q, K, out_pitch;
+  int sstep, ostep;
+  int n_classes;
+  int ti, tj, tn;
+  int tiles_i, tiles_j, tiles_n, tiles_k;
+  int kchunks, w_pitch;
+  int act;
+  float slope;
+  int out_f32, mask_pitch;
+  const float* bias;
+  const float* mask;
+  void* dst;
+  TapTable tt;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_result) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major (or MN-major) tile, 128-byte swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D fp32, A/B bf16, M x N tile, operand majors (0 = K-major, 1 = MN-major)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward / dgrad kernel
+// ------------------------------------------------------------------------------------------------
+template <int TILE_N, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                              const __grid_constant__ CUtensorMap map_b,
+                                                              const __grid_constant__ TcParams p) {
+  constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+  constexpr uint32_t B_BYTES = TILE_N * BLOCK_K * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = TILE_N < 32 ? 32 : TILE_N;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);   // full[S], empty[S], tmem_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- tile coordinates ---------------------------------------------------------------------------
+  int t = blockIdx.x;
+  const int kt = t % p.tiles_k; t /= p.tiles_k;
+  const int jt = t % p.tiles_j; t /= p.tiles_j;
+  const int it = t % p.tiles_i; t /= p.tiles_i;
+  const int nt = t % p.tiles_n;
+  const int cls = t / p.tiles_n;
+  const int py = cls / p.ostep, px = cls - py * p.ostep;
+  const int Pi = (p.P - py + p.ostep - 1) / p.ostep, Qj = (p.Q - px + p.ostep - 1) / p.ostep;
+  const int i0 = it * p.ti, j0 = jt * p.tj, n0 = nt * p.tn, k0 = kt * TILE_N;
+  if (i0 >= Pi || j0 >= Qj) return;   // tile lies outside this (smaller) parity class
+
+  // taps of this class whose source box touches the un-padded input
+  const int ntaps = p.tt.ntaps[cls];
+  auto tap_live = [&](int ti_) -> bool {
+    const int ylo = i0 * p.sstep + p.tt.dy[cls][ti_], yhi = ylo + (p.ti - 1) * p.sstep;
+    const int xlo = j0 * p.sstep + p.tt.dx[cls][ti_], xhi = xlo + (p.tj - 1) * p.sstep;
+    return yhi >= 0 && ylo < p.H && xhi >= 0 && xlo < p.W;
+  };
+  int live = 0;
+  for (int i = 0; i < ntaps; ++i) live += tap_live(i) ? 1 : 0;
+  const int n_iters = live * p.kchunks;
+
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int iter = 0;
+      for (int ti_ = 0; ti_ < ntaps; ++ti_) {
+        if (!tap_live(ti_)) continue;
+        const int y = i0 * p.sstep + p.tt.dy[cls][ti_], x = j0 * p.sstep + p.tt.dx[cls][ti_];
+        const int wcol = p.tt.tap[cls][ti_] * p.w_pitch;
+        for (int kc = 0; kc < p.kchunks; ++kc, ++iter) {
+          const int s = iter % STAGES;
+          mbar_wait(empty_bar(s), ((iter / STAGES) & 1) ^ 1);
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          tma_load_4d(sa, &map_a, full_bar(s), kc * BLOCK_K, x, y, n0);
+          tma_load_2d(sb, &map_b, full_bar(s), wcol + kc * BLOCK_K, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, TILE_N, 0, 0);
+      for (int iter = 0; iter < n_iters; ++iter) {
+        const int s = iter % STAGES;
+        mbar_wait(full_bar(s), (iter / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+        const uint64_t adesc = make_desc(sa, 16, 1024), bdesc = make_desc(sb, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (iter | k) ? 1u : 0u);
+        umma_commit(empty_bar(s));
+      }
+      if (n_iters > 0) umma_commit(tmem_full_bar);
+      else mbar_arrive(tmem_full_bar);
+    }
+  } else {
+    // ===== epilogue: one D row (TMEM lane) per thread =====
+    const int q4 = warp & 3;
+    const int m = q4 * 32 + lane;
+    const int tij = p.ti * p.tj;
+    const int tn_i = m / tij, rem = m - tn_i * tij;
+    const int ti_i = rem / p.tj, tj_i = rem - ti_i * p.tj;
+    const int n = n0 + tn_i, ii = i0 + ti_i, jj = j0 + tj_i;
+    const bool valid = (tn_i < p.tn) && n < p.N && ii < Pi && jj < Qj;
+    const int op = py + ii * p.ostep, oq = px + jj * p.ostep;
+    const int64_t pix = valid ? ((int64_t)n * p.P + op) * p.Q + oq : 0;
+    const float* mrow = (p.mask && valid) ? p.mask + (int64_t)n * p.mask_pitch : nullptr;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < TILE_N; c0 += 16) {
+      if (k0 + c0 >= p.K) break;     // uniform across the CTA
+      uint32_t v[16];
+      if (n_iters > 0) {
+        tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+      if (!valid) continue;
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int k = k0 + c0 + j;
+        float x = __uint_as_float(v[j]);
+        if (k < p.K) {
+          if (p.bias) x += __ldg(p.bias + k);
+          x = icf::apply_act(x, p.act, p.slope);
+          if (mrow) x *= __ldg(mrow + k);
+        }
+        f[j] = x;
+      }
+      const int kbase = k0 + c0;
+      if (p.out_f32) {
+        float* o = reinterpret_cast<float*>(p.dst) + pix * p.out_pitch + kbase;
+        if (kbase + 16 <= p.K && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+          for (int j = 0; j < 16 && kbase + j < p.K; ++j) o[j] = f[j];
+        }
+      } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst) + pix * p.out_pitch + kbase;
+        if (kbase + 16 <= p.K && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+          uint4 a, b;
+          a.x = pack_bf16(f[0], f[1]); a.y = pack_bf16(f[2], f[3]); a.z = pack_bf16(f[4], f[5]); a.w = pack_bf16(f[6], f[7]);
+          b.x = pack_bf16(f[8], f[9]); b.y = pack_bf16(f[10], f[11]); b.z = pack_bf16(f[12], f[13]); b.w = pack_bf16(f[14], f[15]);
+          *reinterpret_cast<uint4*>(o) = a;
+          *reinterpret_cast<uint4*>(o + 8) = b;
+        } else {
+          for (int j = 0; j < 16 && kbase + j < p.K; ++j) o[j] = __float2bfloat16_rn(f[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// per-channel sum / sum of squares of a stored NHWC bf16 tensor (BatchNorm statistics after a tensor-core conv)
+__global__ void col_stats_kernel(const __nv_bfloat16* __restrict__ y, int pitch, int64_t pixels, int C,
+                                 float* __restrict__ stats) {
+  __shared__ float red[2][8][33];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    for (int64_t pix = (int64_t)blockIdx.y * 8 + py; pix < pixels; pix += (int64_t)gridDim.y * 8) {
+      const float v = __bfloat162float(y[pix * pitch + c]);
+      s0 += v;
+      s1 = fmaf(v, v, s1);
+    }
+  }
+  red[0][py][cx] = s0;
+  red[1][py][cx] = s1;
+  __syncthreads();
+  if (py == 0 && c < C) {
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { t0 += red[0][k][cx]; t1 += red[1][k][cx]; }
+    atomicAdd(stats + c, t0);
+    atomicAdd(stats + C + c, t1);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box, const cuuint32_t* estr) {
+  EncodeTiledFn fn = get_encode();
+  ICF_REQUIRE(fn, "tensor-core conv: cuTensorMapEncodeTiled is unavailable");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ICF_REQUIRE(r == CUDA_SUCCESS, "tensor-core conv: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+template <int TILE_N, int STAGES>
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int64_t grid, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + TILE_N * BLOCK_K * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<TILE_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    ICF_REQUIRE(e == cudaSuccess, "tensor-core conv: cannot reserve %zu B of shared memory: %s", smem,
+                cudaGetErrorString(e));
+    configured = true;
+  }
+  conv_tc_kernel<TILE_N, STAGES><<<(unsigned)grid, NUM_THREADS, smem, st>>>(ma, mb, p);
+  return icf::check_launch("conv_tc");
+}
+
+}  // namespace
+
+int icf_tc_conv_forward(const icf_conv_args* a, cudaStream_t st) {
+  // shapes the tensor-core path takes; everything else runs on the direct / SIMT kernels
+  if (a->dtype != ICF_BF16 || a->accumulate) return -1;
+  if (a->C < 16 || a->K < 16) return -1;
+  if ((a->in_pitch & 7) || (a->w_pitch & 7)) return -1;
+  if ((reinterpret_cast<uintptr_t>(a->src) & 15) || (reinterpret_cast<uintptr_t>(a->w) & 15)) return -1;
+  const int taps = a->R * a->S;
+  if (taps > MAX_TAPS || a->stride > 4 || a->pad > 100) return -1;
+  const bool gather = a->form == ICF_FORM_GATHER;
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = a->N; p.H = a->H; p.W = a->W; p.C = a->C;
+  p.P = a->P; p.Q = a->Q; p.K = a->K; p.out_pitch = a->out_pitch;
+  p.sstep = gather ? a->stride : 1;
+  p.ostep = gather ? 1 : a->stride;
+  p.n_classes = p.ostep * p.ostep;
+  if (p.n_classes > MAX_CLASSES) return -1;
+  // tap tables
+  for (int cls = 0; cls < p.n_classes; ++cls) {
+    const int py = cls / p.ostep, px = cls % p.ostep;
+    int n = 0;
+    for (int r = 0; r < a->R; ++r)
+      for (int s = 0; s < a->S; ++s) {
+        int dy, dx;
+        if (gather) {
+          dy = r - a->pad;
+          dx = s - a->pad;
+        } else {
+          const int uy = py + a->pad - r, ux = px + a->pad - s;
+          if (((uy % a->stride) + a->stride) % a->stride != 0 || ((ux % a->stride) + a->stride) % a->stride != 0) continue;
+          dy = uy / a->stride;     // exact (uy is a multiple of stride, possibly negative)
+          dx = ux / a->stride;
+        }
+        if (dy < -128 || dy > 127 || dx < -128 || dx > 127) return -1;
+        p.tt.tap[cls][n] = (int8_t)(r * a->S + s);
+        p.tt.dy[cls][n] = (int8_t)dy;
+        p.tt.dx[cls][n] = (int8_t)dx;
+        ++n;
+      }
+    p.tt.ntaps[cls] = (int16_t)n;
+  }
+  // tile box over the (largest) class index space
+  const int Pi = (a->P + p.ostep - 1) / p.ostep, Qj = (a->Q + p.ostep - 1) / p.ostep;
+  if ((int64_t)Pi * Qj <= BLOCK_M) {
+    p.ti = Pi; p.tj = Qj;
+    p.tn = BLOCK_M / (Pi * Qj);
+    if (p.tn > a->N) p.tn = a->N;
+  } else if (Qj <= BLOCK_M) {
+    p.tj = Qj; p.ti = BLOCK_M / Qj; p.tn = 1;
+  } else {
+    p.tj = BLOCK_M; p.ti = 1; p.tn = 1;
+  }
+  if (p.tj * p.sstep > 256 || p.ti * p.sstep > 256) return -1;
+  p.tiles_i = icf::cdiv(Pi, p.ti);
+  p.tiles_j = icf::cdiv(Qj, p.tj);
+  p.tiles_n = icf::cdiv(a->N, p.tn);
+  p.kchunks = icf::cdiv(a->C, BLOCK_K);
+  p.w_pitch = a->w_pitch;
+  p.act = a->act; p.slope = a->slope; p.out_f32 = a->out_f32; p.mask_pitch = a->mask_pitch;
+  p.bias = a->bias; p.mask = a->out_mask; p.dst = a->dst;
+
+  const int tile_n = a->K > 128 ? 256 : (a->K > 64 ? 128 : (a->K > 32 ? 64 : 32));
+  p.tiles_k = icf::cdiv(a->K, tile_n);
+  const int64_t grid = (int64_t)p.n_classes * p.tiles_n * p.tiles_i * p.tiles_j * p.tiles_k;
+  if (grid > 0x7FFFFFFF) return -1;
+
+  CUtensorMap ma, mb;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)a->C, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N};
+    cuuint64_t str[3] = {(cuuint64_t)a->in_pitch * 2, (cuuint64_t)a->W * a->in_pitch * 2,
+                         (cuuint64_t)a->H * a->W * a->in_pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(p.tj * p.sstep), (cuuint32_t)(p.ti * p.sstep), (cuuint32_t)p.tn};
+    cuuint32_t est[4] = {1, (cuuint32_t)p.sstep, (cuuint32_t)p.sstep, 1};
+    if (int r = encode_map(&ma, a->src, 4, dims, str, box, est)) return r;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)taps * a->w_pitch, (cuuint64_t)a->w_rows};
+    cuuint64_t str[1] = {(cuuint64_t)taps * a->w_pitch * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)tile_n};
+    cuuint32_t est[2] = {1, 1};
+    if (int r = encode_map(&mb, a->w, 2, dims, str, box, est)) return r;
+  }
+  int r;
+  switch (tile_n) {
+    case 256: r = launch_tc<256, 4>(ma, mb, p, grid, st); break;
+    case 128: r = launch_tc<128, 3>(ma, mb, p, grid, st); break;
+    case 64: r = launch_tc<64, 4>(ma, mb, p, grid, st); break;
+    default: r = launch_tc<32, 4>(ma, mb, p, grid, st); break;
+  }
+  if (r) return r;
+  if (a->stats) {
+    const int64_t pixels = (int64_t)a->N * a->P * a->Q;
+    const int groups = icf::cdiv(a->K, 32);
+    int64_t slabs = (148 * 8) / groups;
+    if (slabs > (pixels + 7) / 8) slabs = (pixels + 7) / 8;
+    if (slabs < 1) slabs = 1;
+    if (a->out_f32) { icf::set_error("tensor-core conv: BatchNorm statistics need a bf16 destination"); return 1; }
+    col_stats_kernel<<<dim3(groups, (unsigned)slabs), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a->dst),
+                                                                    a->out_pitch, pixels, a->K, a->stats);
+    return icf::check_launch("col_stats");
+  }
+  return 0;
+}
+
 int icf_tc_conv_wgrad(const icf_wgrad_args*, cudaStream_t) { return -1; }

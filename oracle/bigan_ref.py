@@ -36,20 +36,37 @@ Tensor = torch.Tensor
 # ---------------------------------------------------------------------------------------------
 # generic Sequential interpreter
 # ---------------------------------------------------------------------------------------------
+def bf16_storage(t: Tensor) -> Tensor:
+    """Round to bfloat16 and back with a straight-through gradient.  Passed as ``q`` it turns the oracle into the
+    reference algorithm *with activations and weight operands stored in bf16* (fp32 accumulation, fp32 BatchNorm
+    statistics / losses / Adam) — the arithmetic contract of the CUDA bf16 path.  Needed because LeakyReLU makes
+    gradients discontinuous in the activations: a 5e-3 relative perturbation of the pre-activations flips the
+    sign of ~0.4 % of them, each flip changes that element's derivative 10x (slope 0.1), i.e. a norm-wise
+    gradient difference of ~sqrt(0.004*0.81) = 6 % against an fp32 run for ANY bf16 implementation."""
+    return t + (t.detach().bfloat16().float() - t.detach())
+
+
+_CONTRACTIONS = ("conv", "convT", "linear", "bn")
+
+
 def run_ops(ops, sd: Dict[str, Tensor], x: Tensor, masks: Optional[List[Tensor]] = None,
-            training: bool = True, bn_update: bool = True) -> Tensor:
-    """Execute an op table from ``oracle/arch.py`` with the semantics of the torch layers it names."""
-    for op in ops:
+            training: bool = True, bn_update: bool = True, q=None, q_final: bool = True) -> Tensor:
+    """Execute an op table from ``oracle/arch.py`` with the semantics of the torch layers it names.
+    ``q`` (optional) is applied wherever the CUDA engine stores a tensor: operands (weights), and activations
+    after [conv+activation+dropout] and after [BatchNorm+dropout]."""
+    qq = q if q is not None else (lambda t: t)
+    n_ops = len(ops)
+    for i, op in enumerate(ops):
         kind = op[0]
         if kind == "conv":
             _, key, stride, pad = op
-            x = F.conv2d(x, sd[key + ".weight"], sd[key + ".bias"], stride=stride, padding=pad)
+            x = F.conv2d(x, qq(sd[key + ".weight"]), sd[key + ".bias"], stride=stride, padding=pad)
         elif kind == "convT":
             _, key, stride, pad, opad = op
-            x = F.conv_transpose2d(x, sd[key + ".weight"], sd[key + ".bias"], stride=stride,
+            x = F.conv_transpose2d(x, qq(sd[key + ".weight"]), sd[key + ".bias"], stride=stride,
                                    padding=pad, output_padding=opad)
         elif kind == "linear":
-            x = F.linear(x, sd[op[1] + ".weight"], sd[op[1] + ".bias"])
+            x = F.linear(x, qq(sd[op[1] + ".weight"]), sd[op[1] + ".bias"])
         elif kind == "unflatten":
             x = x.reshape(x.shape[0], *op[1])
         elif kind == "lrelu":
@@ -76,6 +93,10 @@ def run_ops(ops, sd: Dict[str, Tensor], x: Tensor, masks: Optional[List[Tensor]]
                 x = F.batch_norm(x, rm, rv, sd[key + ".weight"], sd[key + ".bias"], False, 0.1, 1e-5)
         else:
             raise ValueError(kind)
+        if q is not None:
+            last = i == n_ops - 1
+            if (last and q_final) or (not last and ops[i + 1][0] in _CONTRACTIONS):
+                x = q(x)
     return x
 
 
@@ -162,26 +183,33 @@ def latent_features(family: str, sd: Dict[str, Tensor], z: Tensor, c: Dict[str, 
 # ---------------------------------------------------------------------------------------------
 # network forwards
 # ---------------------------------------------------------------------------------------------
-def encoder_fwd(family: str, sd, X, c) -> Tensor:
+def _q(q, t):
+    return q(t) if q is not None else t
+
+
+def encoder_fwd(family: str, sd, X, c, q=None) -> Tensor:
     """Encoder.forward (mnist.py:46-56 etc.) -> (N,512,1,1)."""
-    return run_ops(FAMILIES[family]["E"], sd, image_features(family, sd, X, c))
+    return run_ops(FAMILIES[family]["E"], sd, _q(q, image_features(family, sd, X, c)), q=q)
 
 
-def generator_fwd(family: str, sd, z, c) -> Tensor:
+def generator_fwd(family: str, sd, z, c, q=None) -> Tensor:
     """Generator.forward (mnist.py:76-86 etc.) -> (N,1,H,W)."""
-    return run_ops(FAMILIES[family]["G"], sd, latent_features(family, sd, z, c))
+    return run_ops(FAMILIES[family]["G"], sd, _q(q, latent_features(family, sd, z, c)), q=q)
 
 
-def discriminator_fwd(family: str, sd, X, z, c, masks=None, training=True, bn_update=True) -> Tensor:
+def discriminator_fwd(family: str, sd, X, z, c, masks=None, training=True, bn_update=True, q=None) -> Tensor:
     """Discriminator.forward (mnist.py:142-154 etc.) -> logits (N,1)."""
     fam = FAMILIES[family]
     masks = list(masks) if masks is not None else None
     if training and dropout_sites(family) and masks is None:
         raise ValueError("training-mode MNIST discriminator needs explicit dropout masks")
     feats = image_features(family, sd, X, c)
-    dx = run_ops(fam["Dx"], sd, feats, masks, training, bn_update)
-    dz = run_ops(fam["Dz"], sd, z.reshape(-1, fam["latent"], 1, 1), masks, training, bn_update)
-    out = run_ops(fam["Dxz"], sd, torch.cat([dx, dz], dim=1), masks, training, bn_update)
+    zin = z.reshape(-1, fam["latent"], 1, 1)
+    if q is not None and not (training and dropout_sites(family)):
+        feats, zin = q(feats), q(zin)          # with input dropout the engine rounds after the mask (first op)
+    dx = run_ops(fam["Dx"], sd, feats, masks, training, bn_update, q=q)
+    dz = run_ops(fam["Dz"], sd, zin, masks, training, bn_update, q=q)
+    out = run_ops(fam["Dxz"], sd, torch.cat([dx, dz], dim=1), masks, training, bn_update, q=q, q_final=False)
     return out.reshape(-1, 1)
 
 
@@ -235,8 +263,9 @@ def _leaf_params(sd):
 class BiGANOracle:
     """Holds E/G/D state dicts + two Adam states and replays the reference loop body."""
 
-    def __init__(self, family: str, E_sd, G_sd, D_sd, lr=1e-4, betas=None):
+    def __init__(self, family: str, E_sd, G_sd, D_sd, lr=1e-4, betas=None, q=None):
         self.family = family
+        self.q = q                  # None = the fp32 reference; bf16_storage = bf16-storage arithmetic contract
         fam = FAMILIES[family]
         betas = betas if betas is not None else fam["adam_betas"]
 
@@ -278,8 +307,8 @@ class BiGANOracle:
         if phase_a:
             self._zero(self.pE)
             self._zero(self.pD)
-            D_valid = discriminator_fwd(fam, self.D, images, encoder_fwd(fam, self.E, images, c), c, masks6[0])
-            D_fake = discriminator_fwd(fam, self.D, generator_fwd(fam, self.G, z, c), z, c, masks6[1])
+            D_valid = discriminator_fwd(fam, self.D, images, encoder_fwd(fam, self.E, images, c, q=self.q), c, masks6[0], q=self.q)
+            D_fake = discriminator_fwd(fam, self.D, generator_fwd(fam, self.G, z, c, q=self.q), z, c, masks6[1], q=self.q)
             loss_EG = (bce_with_logits(D_valid, fake) + bce_with_logits(D_fake, valid)) / 2
             loss_EG.backward()
             if keep_grads:
@@ -288,7 +317,7 @@ class BiGANOracle:
             out["loss_EG"] = float(loss_EG)
         # Phase B — D on real pairs (mnist.py:232-236)
         self._zero(self.pD)
-        D_valid = discriminator_fwd(fam, self.D, images, encoder_fwd(fam, self.E, images, c), c, masks6[2])
+        D_valid = discriminator_fwd(fam, self.D, images, encoder_fwd(fam, self.E, images, c, q=self.q), c, masks6[2], q=self.q)
         loss_D = bce_with_logits(D_valid, valid)
         loss_D.backward()
         if keep_grads:
@@ -297,7 +326,7 @@ class BiGANOracle:
         out["loss_D_valid"] = float(loss_D)
         # Phase C — D on generated pairs (mnist.py:237-241)
         self._zero(self.pD)
-        D_fake = discriminator_fwd(fam, self.D, generator_fwd(fam, self.G, z, c), z, c, masks6[3])
+        D_fake = discriminator_fwd(fam, self.D, generator_fwd(fam, self.G, z, c, q=self.q), z, c, masks6[3], q=self.q)
         loss_D = bce_with_logits(D_fake, fake)
         loss_D.backward()
         if keep_grads:
@@ -306,10 +335,10 @@ class BiGANOracle:
         out["loss_D_fake"] = float(loss_D)
         # Phase D — scores (mnist.py:243-248); D stays in train mode (dropout + BN stat updates)
         with torch.no_grad():
-            Gz = generator_fwd(fam, self.G, z, c)
-            EX = encoder_fwd(fam, self.E, images, c)
-            DG = discriminator_fwd(fam, self.D, Gz, z, c, masks6[4]).sigmoid()
-            DE = discriminator_fwd(fam, self.D, images, EX, c, masks6[5]).sigmoid()
+            Gz = generator_fwd(fam, self.G, z, c, q=self.q)
+            EX = encoder_fwd(fam, self.E, images, c, q=self.q)
+            DG = discriminator_fwd(fam, self.D, Gz, z, c, masks6[4], q=self.q).sigmoid()
+            DE = discriminator_fwd(fam, self.D, images, EX, c, masks6[5], q=self.q).sigmoid()
         out["DG_mean"] = float(DG.mean())
         out["DE_mean"] = float(DE.mean())
         self._zero(self.pE)
