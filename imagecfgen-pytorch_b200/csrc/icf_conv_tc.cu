@@ -21,7 +21,7 @@ namespace {
 constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
 constexpr int MAX_CLASSES = 16, MAX_TAPS = 25;
 constexpr int NUM_THREADS = 192;
-constexpr uint32_t SPIN_LIMIT = 1u << 26;   // a wedged pipeline traps instead of hanging the GPU
+constexpr long long SPIN_CYCLES = 4000000000LL;   // ~2 s: a wedged pipeline traps instead of hanging the GPU
 
 struct TapTable {
   int16_t ntaps[MAX_CLASSES];
@@ -38,6 +38,7 @@ struct TcParams {
   int ti, tj, tn;
   int tiles_i, tiles_j, tiles_n, tiles_k;
   int kchunks, w_pitch;
+  uint32_t a_tx_bytes;          // bytes one A box deposits: tn*ti*tj rows of 128 B
   int act;
   float slope;
   int out_f32, mask_pitch;
@@ -73,9 +74,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > SPIN_LIMIT) __trap();
+    if (clock64() - t0 > SPIN_CYCLES) {
+      printf("icf conv_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
           const int s = iter % STAGES;
           mbar_wait(empty_bar(s), ((iter / STAGES) & 1) ^ 1);
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
-          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          mbar_expect_tx(full_bar(s), p.a_tx_bytes + B_BYTES);
           tma_load_4d(sa, &map_a, full_bar(s), kc * BLOCK_K, x, y, n0);
           tma_load_2d(sb, &map_b, full_bar(s), wcol + kc * BLOCK_K, k0);
         }
@@ -449,6 +454,7 @@ int icf_tc_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   p.tiles_n = icf::cdiv(a->N, p.tn);
   p.kchunks = icf::cdiv(a->C, BLOCK_K);
   p.w_pitch = a->w_pitch;
+  p.a_tx_bytes = (uint32_t)(p.tn * p.ti * p.tj) * (BLOCK_K * 2);
   p.act = a->act; p.slope = a->slope; p.out_f32 = a->out_f32; p.mask_pitch = a->mask_pitch;
   p.bias = a->bias; p.mask = a->out_mask; p.dst = a->dst;
 
