@@ -240,12 +240,30 @@ def run_ours(args):
         tr.step(images, c)
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
-        for name, e0, e1, fl, nb in prof:
+        layers = {}
+        for name, e0, e1, fl, nb, det in prof:
+            ms = e0.elapsed_time(e1)
             k = kern.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
-            k["ms"] += e0.elapsed_time(e1)
+            k["ms"] += ms
             k["n"] += 1
             k["flops"] += fl
             k["bytes"] += nb
+            if det:
+                d = layers.setdefault(det, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
+                d["ms"] += ms
+                d["n"] += 1
+                d["flops"] += fl
+                d["bytes"] += nb
+        pk0 = peaks()
+        per_layer = []
+        for det, d in sorted(layers.items(), key=lambda kv: -kv[1]["ms"]):
+            sec = d["ms"] * 1e-3
+            t_roof = max(d["flops"] / (pk0["tf_sust"] * 1e12), d["bytes"] / (pk0["hbm"] * 1e9))
+            per_layer.append({"layer": det, "n": d["n"], "ms": round(d["ms"], 4),
+                              "tflops": round(d["flops"] / sec / 1e12, 2), "gbs": round(d["bytes"] / sec / 1e9, 1),
+                              "roofline_frac": round(t_roof / sec, 4)})
+        with open(os.path.join(ROOT, "gpurun_out", "per_layer.json") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else os.devnull, "w") as f:
+            json.dump(per_layer, f, indent=1)
         total = sum(k["ms"] for k in kern.values())
         pk = peaks()
         conv = {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0}

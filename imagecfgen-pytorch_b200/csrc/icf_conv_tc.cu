@@ -324,6 +324,135 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// weight-gradient kernel:  dw[a][tap][b] += sum_{pixels m} small[m][a] * big[pix(m, tap)][b]
+// Both operands are [pixels][channels] tensors, i.e. MN-major for the MMA (the reduction runs over pixels).
+// A K-block is a BOX (bn images x bp rows x bq columns, bn*bp*bq in {16,32,48,64}) of the small tensor's pixel
+// grid, over-covering it where needed: out-of-range pixels of `small` are zero-filled by TMA, which also
+// cancels whatever the matching `big` box holds there.  One CTA owns one (a-tile, b-tile, tap) and a strided
+// subset of the K-blocks, accumulates in TMEM and adds its partial tile into dw with fp32 atomics.
+// ------------------------------------------------------------------------------------------------
+struct WgParams {
+  int N, P, Q, A;          // small: [N][P][Q][a_pitch]
+  int H, W, B;             // big:   [N][H][W][b_pitch]
+  int S, stride, pad, taps;
+  int bq, bp, bn;          // K-block box
+  int blocks_q, blocks_p, blocks_n;
+  int a_tiles, b_tiles;
+  uint32_t rows;           // bq*bp*bn
+  float* dw;
+};
+
+template <int TILE_N, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_s,
+                                                               const __grid_constant__ CUtensorMap map_g,
+                                                               const __grid_constant__ WgParams p) {
+  constexpr uint32_t CHUNK_BYTES = 64 * 64 * 2;                  // one 64-channel x 64-pixel chunk (max rows)
+  constexpr int NB = TILE_N / 64;                                // B chunks
+  constexpr uint32_t STAGE_BYTES = (2 + NB) * CHUNK_BYTES;
+  constexpr int TMEM_COLS = TILE_N < 32 ? 32 : TILE_N;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int t = blockIdx.x;
+  const int tap = t % p.taps; t /= p.taps;
+  const int bt = t % p.b_tiles;
+  const int at = t / p.b_tiles;
+  const int r = tap / p.S, s = tap - r * p.S;
+  const int a0 = at * BLOCK_M, b0 = bt * TILE_N;
+  const int n_blocks = p.blocks_q * p.blocks_p * p.blocks_n;
+  const int split = blockIdx.y, splits = gridDim.y;
+  const int my_blocks = split < n_blocks ? (n_blocks - split + splits - 1) / splits : 0;
+
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int st) { return bar_base + 8u * st; };
+  auto empty_bar = [&](int st) { return bar_base + 8u * (STAGES + st); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_s);
+    prefetch_tmap(&map_g);
+    for (int st = 0; st < STAGES; ++st) {
+      mbar_init(full_bar(st), 1);
+      mbar_init(empty_bar(st), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t chunk_bytes = p.rows * 128u;                    // bytes one box deposits
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < my_blocks; ++i) {
+        int blk = split + i * splits;
+        const int qb = blk % p.blocks_q; blk /= p.blocks_q;
+        const int pb = blk % p.blocks_p;
+        const int nb = blk / p.blocks_p;
+        const int q0 = qb * p.bq, p0 = pb * p.bp, n0 = nb * p.bn;
+        const int st = i % STAGES;
+        mbar_wait(empty_bar(st), ((i / STAGES) & 1) ^ 1);
+        const uint32_t base = smem_u32(smem + st * STAGE_BYTES);
+        mbar_expect_tx(full_bar(st), chunk_bytes * (2 + NB));
+        tma_load_4d(base, &map_s, full_bar(st), a0, q0, p0, n0);
+        tma_load_4d(base + CHUNK_BYTES, &map_s, full_bar(st), a0 + 64, q0, p0, n0);
+        const int x = q0 * p.stride - p.pad + s, y = p0 * p.stride - p.pad + r;
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          tma_load_4d(base + (2 + j) * CHUNK_BYTES, &map_g, full_bar(st), b0 + 64 * j, x, y, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, TILE_N, 1, 1);
+      const int ksteps = (int)p.rows / UMMA_K;
+      for (int i = 0; i < my_blocks; ++i) {
+        const int st = i % STAGES;
+        mbar_wait(full_bar(st), (i / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + st * STAGE_BYTES);
+        // MN-major, 128B swizzle: 64-channel chunks CHUNK_BYTES apart (LBO), 8-pixel groups 1024 B apart (SBO)
+        const uint64_t adesc = make_desc(base, CHUNK_BYTES, 1024), bdesc = make_desc(base + 2 * CHUNK_BYTES, CHUNK_BYTES, 1024);
+        for (int k = 0; k < ksteps; ++k)   // 16 pixels = 2048 B = 128 descriptor units per step
+          umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (i | k) ? 1u : 0u);
+        umma_commit(empty_bar(st));
+      }
+      if (my_blocks > 0) umma_commit(tmem_full_bar);
+      else mbar_arrive(tmem_full_bar);
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int a = a0 + q4 * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    if (my_blocks > 0) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < TILE_N; c0 += 16) {
+        if (b0 + c0 >= p.B) break;
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (a < p.A) {
+          float* o = p.dw + ((int64_t)a * p.taps + tap) * p.B + b0 + c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (b0 + c0 + j < p.B) atomicAdd(o + j, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
 // per-channel sum / sum of squares of a stored NHWC bf16 tensor (BatchNorm statistics after a tensor-core conv)
 __global__ void col_stats_kernel(const __nv_bfloat16* __restrict__ y, int pitch, int64_t pixels, int C,
                                  float* __restrict__ stats) {
@@ -501,4 +630,102 @@ int icf_tc_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   return 0;
 }
 
-int icf_tc_conv_wgrad(const icf_wgrad_args*, cudaStream_t) { return -1; }
+
+namespace {
+
+template <int TILE_N, int STAGES>
+int launch_wg(const CUtensorMap& ms, const CUtensorMap& mg, const WgParams& p, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (2 + TILE_N / 64) * 8192 + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<TILE_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    ICF_REQUIRE(e == cudaSuccess, "tensor-core wgrad: cannot reserve %zu B of shared memory: %s", smem,
+                cudaGetErrorString(e));
+    configured = true;
+  }
+  wgrad_tc_kernel<TILE_N, STAGES><<<grid, NUM_THREADS, smem, st>>>(ms, mg, p);
+  return icf::check_launch("wgrad_tc");
+}
+
+// K-block box (bq, bp, bn) over the small tensor's pixel grid: rows = bq*bp*bn in {16,32,48,64}, chosen to waste
+// as few zero-filled rows as possible
+void pick_kblock(int N, int P, int Q, int* bq_, int* bp_, int* bn_) {
+  double best = -1.0;
+  int best_rows = 0;
+  for (int bq = 1; bq <= 64; ++bq) {
+    if (bq > Q + 15) break;
+    for (int bp = 1; bp * bq <= 64; ++bp) {
+      if (bp > P + 15) break;
+      for (int bn = 1; bn * bp * bq <= 64; ++bn) {
+        if (bn > N && bn > 1) break;
+        const int rows = bq * bp * bn;
+        if (rows % 16) continue;
+        const double covered = (double)icf::cdiv(Q, bq) * bq * icf::cdiv(P, bp) * bp * icf::cdiv(N, bn) * bn;
+        const double eff = (double)N * P * Q / covered;
+        if (eff > best + 1e-9 || (eff > best - 1e-9 && rows > best_rows)) {
+          best = eff; best_rows = rows;
+          *bq_ = bq; *bp_ = bp; *bn_ = bn;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int icf_tc_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
+  if (a->dtype != ICF_BF16) return -1;
+  if (a->A < 16 || a->B < 16) return -1;
+  if ((a->a_pitch & 7) || (a->b_pitch & 7)) return -1;
+  if ((reinterpret_cast<uintptr_t>(a->small_t) & 15) || (reinterpret_cast<uintptr_t>(a->big_t) & 15)) return -1;
+  if (a->stride > 4) return -1;
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = a->N; p.P = a->P; p.Q = a->Q; p.A = a->A;
+  p.H = a->H; p.W = a->W; p.B = a->B;
+  p.S = a->S; p.stride = a->stride; p.pad = a->pad; p.taps = a->R * a->S;
+  p.bq = p.bp = p.bn = 0;
+  pick_kblock(a->N, a->P, a->Q, &p.bq, &p.bp, &p.bn);
+  if (p.bq == 0) return -1;
+  if (p.bq * a->stride > 256 || p.bp * a->stride > 256) return -1;
+  p.rows = (uint32_t)(p.bq * p.bp * p.bn);
+  p.blocks_q = icf::cdiv(a->Q, p.bq);
+  p.blocks_p = icf::cdiv(a->P, p.bp);
+  p.blocks_n = icf::cdiv(a->N, p.bn);
+  const int tile_n = a->B > 128 ? 256 : (a->B > 64 ? 128 : 64);
+  p.a_tiles = icf::cdiv(a->A, BLOCK_M);
+  p.b_tiles = icf::cdiv(a->B, tile_n);
+  p.dw = a->dw;
+  const int64_t n_blocks = (int64_t)p.blocks_q * p.blocks_p * p.blocks_n;
+  if (n_blocks > 0x7FFFFFFF) return -1;
+  const int64_t tiles = (int64_t)p.a_tiles * p.b_tiles * p.taps;
+  int64_t splits = (148 * 2 + tiles - 1) / tiles;       // ~2 CTAs per SM in flight
+  if (splits > n_blocks) splits = n_blocks;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  CUtensorMap ms, mg;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)a->A, (cuuint64_t)a->Q, (cuuint64_t)a->P, (cuuint64_t)a->N};
+    cuuint64_t str[3] = {(cuuint64_t)a->a_pitch * 2, (cuuint64_t)a->Q * a->a_pitch * 2,
+                         (cuuint64_t)a->P * a->Q * a->a_pitch * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.bq, (cuuint32_t)p.bp, (cuuint32_t)p.bn};
+    cuuint32_t est[4] = {1, 1, 1, 1};
+    if (int r = encode_map(&ms, a->small_t, 4, dims, str, box, est)) return r;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)a->B, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N};
+    cuuint64_t str[3] = {(cuuint64_t)a->b_pitch * 2, (cuuint64_t)a->W * a->b_pitch * 2,
+                         (cuuint64_t)a->H * a->W * a->b_pitch * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(p.bq * a->stride), (cuuint32_t)(p.bp * a->stride), (cuuint32_t)p.bn};
+    cuuint32_t est[4] = {1, (cuuint32_t)a->stride, (cuuint32_t)a->stride, 1};
+    if (int r = encode_map(&mg, a->big_t, 4, dims, str, box, est)) return r;
+  }
+  dim3 grid((unsigned)tiles, (unsigned)splits);
+  switch (tile_n) {
+    case 256: return launch_wg<256, 3>(ms, mg, p, grid, st);
+    case 128: return launch_wg<128, 3>(ms, mg, p, grid, st);
+    default: return launch_wg<64, 4>(ms, mg, p, grid, st);
+  }
+}
+

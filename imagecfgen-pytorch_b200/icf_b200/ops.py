@@ -52,7 +52,7 @@ LAUNCHES = 0          # C-ABI launch calls made so far (bench.py reports the per
 PROFILE = None        # set to a list to record (name, start_event, end_event, flops, bytes) per launch
 
 
-def _launch(name, fn, *args, flops=0.0, nbytes=0.0):
+def _launch(name, fn, *args, flops=0.0, nbytes=0.0, detail=""):
     global LAUNCHES
     LAUNCHES += 1
     if PROFILE is not None:
@@ -60,7 +60,7 @@ def _launch(name, fn, *args, flops=0.0, nbytes=0.0):
         e0.record()
         st = fn(*args, stream())
         e1.record()
-        PROFILE.append((name, e0, e1, flops, nbytes))
+        PROFILE.append((name, e0, e1, flops, nbytes, detail))
     else:
         st = fn(*args, stream())
     _l.check(st, name)
@@ -83,11 +83,13 @@ def conv_forward(dtype, form, N, H, W, Cc, in_pitch, P, Q, K, out_pitch, R, S, s
                     w_rows, w_pitch, ACT[act], slope, 1 if out_f32 else 0, mask_pitch,
                     1 if accumulate else 0, src, w, bias, dst, mask, stats)
     fl = nb = 0.0
+    det = ""
     if PROFILE is not None:
         es = 4 if dtype == F32 else 2
         fl = 2.0 * N * Cc * K * valid_taps(form, H, P, R, stride, pad) * valid_taps(form, W, Q, S, stride, pad)
         nb = float(es) * (N * (H * W * Cc + P * Q * K) + K * Cc * R * S)
-    _launch("icf_conv_forward", _l.load().icf_conv_forward, C.byref(a), flops=fl, nbytes=nb)
+        det = f"{'gather' if form == GATHER else 'transp'} {Cc}x{H}x{W}->{K}x{P}x{Q} k{R}s{stride}p{pad}"
+    _launch("icf_conv_forward", _l.load().icf_conv_forward, C.byref(a), flops=fl, nbytes=nb, detail=det)
 
 
 def conv_wgrad(dtype, N, P, Q, A, a_pitch, H, W, B, b_pitch, R, S, stride, pad, small, big, dw):
@@ -97,7 +99,8 @@ def conv_wgrad(dtype, N, P, Q, A, a_pitch, H, W, B, b_pitch, R, S, stride, pad, 
         es = 4 if dtype == F32 else 2
         fl = 2.0 * N * A * B * valid_taps(GATHER, H, P, R, stride, pad) * valid_taps(GATHER, W, Q, S, stride, pad)
         nb = float(es) * N * (H * W * B + P * Q * A) + 4.0 * A * B * R * S
-    _launch("icf_conv_wgrad", _l.load().icf_conv_wgrad, C.byref(a), flops=fl, nbytes=nb)
+    det = f"wgrad A{A}x{P}x{Q} B{B}x{H}x{W} k{R}s{stride}p{pad}" if PROFILE is not None else ""
+    _launch("icf_conv_wgrad", _l.load().icf_conv_wgrad, C.byref(a), flops=fl, nbytes=nb, detail=det)
 
 
 def make_perm(d0, d1, d2, s0, s1, s2, d2_pad=None, d0_pad=None):
