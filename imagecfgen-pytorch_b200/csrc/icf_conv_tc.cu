@@ -527,7 +527,8 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, i
 int icf_tc_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   // shapes the tensor-core path takes; everything else runs on the direct / SIMT kernels
   if (a->dtype != ICF_BF16 || a->accumulate) return -1;
-  if (a->C < 16 || a->K < 16) return -1;
+  // small-channel first / last layers ride the same kernel: TMA zero-fills the missing channels of the 64-wide
+  // K chunk, so they cost tensor time but only their real bytes of HBM traffic (they are HBM-bound layers)
   if ((a->in_pitch & 7) || (a->w_pitch & 7)) return -1;
   if ((reinterpret_cast<uintptr_t>(a->src) & 15) || (reinterpret_cast<uintptr_t>(a->w) & 15)) return -1;
   const int taps = a->R * a->S;
@@ -676,7 +677,6 @@ void pick_kblock(int N, int P, int Q, int* bq_, int* bp_, int* bn_) {
 
 int icf_tc_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
   if (a->dtype != ICF_BF16) return -1;
-  if (a->A < 16 || a->B < 16) return -1;
   if ((a->a_pitch & 7) || (a->b_pitch & 7)) return -1;
   if ((reinterpret_cast<uintptr_t>(a->small_t) & 15) || (reinterpret_cast<uintptr_t>(a->big_t) & 15)) return -1;
   if (a->stride > 4) return -1;

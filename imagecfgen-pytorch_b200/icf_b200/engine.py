@@ -342,11 +342,11 @@ class NetExec:
             om = rec["out_mask"]
             om_ptr, om_pitch = (om[1], om[2]) if om is not None else (None, 0)
             # dPre in the compute dtype; reuse g's storage when it is ours, same dtype and same pitch
-            if inplace_ok and g.t.dtype == self.dt and g.off == 0 and g.pitch == (pad8(le.Cout) if le.Cout > 1 else 1):
+            # (pitch is always a multiple of 8 so that single-channel gradients stay TMA-addressable)
+            if inplace_ok and g.t.dtype == self.dt and g.off == 0 and g.pitch == pad8(le.Cout):
                 dpre = Act(g.t, le.Cout)
             else:
-                dpre = Act(torch.empty((pix, pad8(le.Cout) if le.Cout > 1 else 1), dtype=self.dt, device=self.device),
-                           le.Cout)
+                dpre = Act(torch.empty((pix, pad8(le.Cout)), dtype=self.dt, device=self.device), le.Cout)
             dpitch = dpre.pitch * pps if sp.kind == "linear" else dpre.pitch
             if grads is not None:
                 if le.perm_bias is None:

@@ -8,6 +8,9 @@ CASES = [  # kind, N, C, H, K, k, stride, pad, opad
     ("conv", 20, 256, 3, 512, 4, 2, 1, 0), ("conv", 2, 32, 24, 64, 4, 2, 0, 0), ("conv", 2, 64, 31, 128, 5, 2, 1, 0),
     ("convT", 3, 771, 1, 512, 3, 1, 0, 0), ("convT", 2, 512, 3, 256, 3, 2, 0, 0), ("convT", 2, 256, 7, 128, 3, 2, 1, 0),
     ("convT", 2, 128, 13, 64, 3, 2, 1, 0), ("convT", 2, 64, 4, 32, 5, 2, 2, 1), ("convT", 2, 1024, 4, 512, 5, 2, 2, 1),
+    ("conv", 3, 5, 28, 32, 5, 1, 0, 0), ("conv", 3, 5, 28, 64, 3, 2, 1, 0), ("conv", 2, 7, 64, 64, 5, 2, 1, 0),
+    ("convT", 3, 64, 25, 1, 4, 1, 0, 0), ("convT", 2, 64, 16, 1, 5, 2, 2, 1), ("convT", 3, 32, 24, 5, 5, 1, 0, 0),
+    ("conv", 3, 1, 28, 64, 4, 1, 0, 0), ("conv", 200, 1024, 1, 1, 1, 1, 0, 0),
 ]
 
 
@@ -17,6 +20,8 @@ WG_CASES = [  # kind, N, C(in), H, K(out), k, stride, pad, opad
     ("conv", 3, 64, 11, 128, 4, 1, 0, 0), ("conv", 2, 64, 31, 128, 5, 2, 1, 0),
     ("convT", 5, 771, 1, 512, 3, 1, 0, 0), ("convT", 3, 512, 3, 256, 3, 2, 0, 0), ("convT", 2, 256, 7, 128, 3, 2, 1, 0),
     ("convT", 2, 128, 13, 64, 3, 2, 1, 0), ("convT", 2, 1024, 4, 512, 5, 2, 2, 1),
+    ("conv", 3, 5, 28, 32, 5, 1, 0, 0), ("conv", 3, 5, 28, 64, 3, 2, 1, 0), ("convT", 3, 64, 25, 1, 4, 1, 0, 0),
+    ("conv", 70, 1024, 1, 1, 1, 1, 0, 0), ("conv", 2, 7, 64, 64, 5, 2, 1, 0),
 ]
 
 
