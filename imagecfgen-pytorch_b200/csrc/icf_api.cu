@@ -58,7 +58,10 @@ static int validate_conv(const icf_conv_args* a) {
   ICF_REQUIRE(a->N >= 0 && a->H > 0 && a->W > 0 && a->C > 0 && a->P > 0 && a->Q > 0 && a->K > 0 && a->R > 0 &&
                   a->S > 0 && a->stride > 0 && a->pad >= 0,
               "icf_conv_forward: non-positive extent");
-  ICF_REQUIRE(a->in_pitch >= a->C && a->out_pitch >= a->K && a->w_rows >= a->K && a->w_pitch >= a->C,
+  if (a->win > 1)
+    ICF_REQUIRE(a->S == 1 && a->C == a->win * a->in_pitch && a->form == ICF_FORM_GATHER && a->dtype == ICF_BF16,
+                "icf_conv_forward: folded (win) form needs S=1, C=win*in_pitch, gather form, bf16");
+  ICF_REQUIRE((a->win > 1 || a->in_pitch >= a->C) && a->out_pitch >= a->K && a->w_rows >= a->K && a->w_pitch >= a->C,
               "icf_conv_forward: pitch/rows smaller than channel count (C=%d pitch=%d, K=%d pitch=%d rows=%d)",
               a->C, a->in_pitch, a->K, a->out_pitch, a->w_rows);
   ICF_REQUIRE(!a->accumulate || a->out_f32 || a->dtype == ICF_F32, "icf_conv_forward: accumulate needs f32 dst");
@@ -73,6 +76,7 @@ int icf_conv_forward(const icf_conv_args* a, void* stream) {
     int r = icf_tc_conv_forward(a, st);
     if (r >= 0) return r;
   }
+  ICF_REQUIRE(a->win <= 1, "icf_conv_forward: the folded (win) form exists only on the tensor-core path");
   return icf_simt_conv_forward(a, st);
 }
 
@@ -81,7 +85,8 @@ int icf_conv_wgrad(const icf_wgrad_args* a, void* stream) {
   ICF_REQUIRE(a->dtype == ICF_F32 || a->dtype == ICF_BF16, "icf_conv_wgrad: dtype %d", a->dtype);
   ICF_REQUIRE(a->small_t && a->big_t && a->dw, "icf_conv_wgrad: null tensor pointer");
   ICF_REQUIRE(a->N >= 0 && a->P > 0 && a->Q > 0 && a->A > 0 && a->H > 0 && a->W > 0 && a->B > 0 && a->R > 0 &&
-                  a->S > 0 && a->stride > 0 && a->pad >= 0 && a->a_pitch >= a->A && a->b_pitch >= a->B,
+                  a->S > 0 && a->stride > 0 && a->pad >= 0 && a->a_pitch >= a->A &&
+                  (a->win > 1 ? (a->S == 1 && a->B == a->win * a->b_pitch) : a->b_pitch >= a->B),
               "icf_conv_wgrad: bad extents");
   if (a->N == 0) return 0;
   cudaStream_t st = icf::as_stream(stream);
@@ -89,6 +94,7 @@ int icf_conv_wgrad(const icf_wgrad_args* a, void* stream) {
     int r = icf_tc_conv_wgrad(a, st);
     if (r >= 0) return r;
   }
+  ICF_REQUIRE(a->win <= 1, "icf_conv_wgrad: the folded (win) form exists only on the tensor-core path");
   return icf_simt_conv_wgrad(a, st);
 }
 

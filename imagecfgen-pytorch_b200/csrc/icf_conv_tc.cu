@@ -453,32 +453,6 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-// per-channel sum / sum of squares of a stored NHWC bf16 tensor (BatchNorm statistics after a tensor-core conv)
-__global__ void col_stats_kernel(const __nv_bfloat16* __restrict__ y, int pitch, int64_t pixels, int C,
-                                 float* __restrict__ stats) {
-  __shared__ float red[2][8][33];
-  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
-  float s0 = 0.f, s1 = 0.f;
-  if (c < C) {
-    for (int64_t pix = (int64_t)blockIdx.y * 8 + py; pix < pixels; pix += (int64_t)gridDim.y * 8) {
-      const float v = __bfloat162float(y[pix * pitch + c]);
-      s0 += v;
-      s1 = fmaf(v, v, s1);
-    }
-  }
-  red[0][py][cx] = s0;
-  red[1][py][cx] = s1;
-  __syncthreads();
-  if (py == 0 && c < C) {
-    float t0 = 0.f, t1 = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { t0 += red[0][k][cx]; t1 += red[1][k][cx]; }
-    atomicAdd(stats + c, t0);
-    atomicAdd(stats + C + c, t1);
-  }
-}
-
 // ---- host side ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -530,6 +504,7 @@ int icf_tc_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   // small-channel first / last layers ride the same kernel: TMA zero-fills the missing channels of the 64-wide
   // K chunk, so they cost tensor time but only their real bytes of HBM traffic (they are HBM-bound layers)
   if ((a->in_pitch & 7) || (a->w_pitch & 7)) return -1;
+  if (a->win > 1 && a->pad != 0) return -1;   // the folded form reads a pre-padded tensor
   if ((reinterpret_cast<uintptr_t>(a->src) & 15) || (reinterpret_cast<uintptr_t>(a->w) & 15)) return -1;
   const int taps = a->R * a->S;
   if (taps > MAX_TAPS || a->stride > 4 || a->pad > 100) return -1;
@@ -618,15 +593,8 @@ int icf_tc_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   }
   if (r) return r;
   if (a->stats) {
-    const int64_t pixels = (int64_t)a->N * a->P * a->Q;
-    const int groups = icf::cdiv(a->K, 32);
-    int64_t slabs = (148 * 8) / groups;
-    if (slabs > (pixels + 7) / 8) slabs = (pixels + 7) / 8;
-    if (slabs < 1) slabs = 1;
     if (a->out_f32) { icf::set_error("tensor-core conv: BatchNorm statistics need a bf16 destination"); return 1; }
-    col_stats_kernel<<<dim3(groups, (unsigned)slabs), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a->dst),
-                                                                    a->out_pitch, pixels, a->K, a->stats);
-    return icf::check_launch("col_stats");
+    return icf_launch_col_stats(a->dst, ICF_BF16, a->out_pitch, (int64_t)a->N * a->P * a->Q, a->K, a->stats, st);
   }
   return 0;
 }

@@ -36,28 +36,34 @@ __global__ void argmax_rows_kernel(const void* x, int dt, int n, int k, int32_t*
 // one thread per pixel writes the whole (<= 8 channel) vector
 // ------------------------------------------------------------------------------------------------
 __global__ void imgfeat_fwd_kernel(const icf_imgfeat_args a) {
-  const int64_t total = (int64_t)a.N * a.H * a.W;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int hw = a.H * a.W;
-  const int n = (int)(i / hw);
-  const int rem = (int)(i - (int64_t)n * hw);
-  const int y = rem / a.W, x = rem - y * a.W;
+  const int Hp = a.H + 2 * a.pad, Wp = a.W + 2 * a.pad;
+  const int64_t total = (int64_t)a.N * Hp * Wp;
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // padded output pixel
+  if (o >= total) return;
+  const int hwp = Hp * Wp;
+  const int n = (int)(o / hwp);
+  const int remp = (int)(o - (int64_t)n * hwp);
+  const int y = remp / Wp - a.pad, x = remp % Wp - a.pad;
+  if (y < 0 || y >= a.H || x < 0 || x >= a.W) {                        // zero border
+    for (int ch = 0; ch < a.feat_pitch; ++ch) icf::st_any(a.feat, a.dtype, o * a.feat_pitch + ch, 0.f);
+    return;
+  }
+  const int64_t i = ((int64_t)n * a.H + y) * a.W + x;                  // source pixel
   const int cy = min((y * 16) / a.H, 15), cx = min((x * 16) / a.W, 15);   // nearest: floor(dst*16/size)
   const float* mk = a.mask ? a.mask + (int64_t)n * a.mask_pitch : nullptr;
   int ch = 0;
   float v = icf::ld_any(a.x, a.x_dtype, i * a.x_pitch);
-  icf::st_any(a.feat, a.dtype, i * a.feat_pitch + ch, mk ? v * mk[ch] : v);
+  icf::st_any(a.feat, a.dtype, o * a.feat_pitch + ch, mk ? v * mk[ch] : v);
   ++ch;
   for (int e = 0; e < a.n_emb; ++e, ++ch) {
     const float t = tanhf(a.emb_table[e][(int64_t)a.emb_index[e][n] * 256 + cy * 16 + cx]);
-    icf::st_any(a.feat, a.dtype, i * a.feat_pitch + ch, mk ? t * mk[ch] : t);
+    icf::st_any(a.feat, a.dtype, o * a.feat_pitch + ch, mk ? t * mk[ch] : t);
   }
   for (int e = 0; e < a.n_cont; ++e, ++ch) {
     const float t = a.cont[e][n];
-    icf::st_any(a.feat, a.dtype, i * a.feat_pitch + ch, mk ? t * mk[ch] : t);
+    icf::st_any(a.feat, a.dtype, o * a.feat_pitch + ch, mk ? t * mk[ch] : t);
   }
-  for (; ch < a.feat_pitch; ++ch) icf::st_any(a.feat, a.dtype, i * a.feat_pitch + ch, 0.f);
+  for (; ch < a.feat_pitch; ++ch) icf::st_any(a.feat, a.dtype, o * a.feat_pitch + ch, 0.f);
 }
 
 // gradient into the embedding tables: one warp per (sample, plane, cell): reduce the cell's pixel block
@@ -291,6 +297,244 @@ __global__ void act_backward_kernel(const icf_actbwd_args a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 8-channel vector variants (bf16: one 16-byte access, fp32: two) of the HBM-bound passes.  A thread keeps
+// the same channel group for its whole pixel loop, so per-channel parameters and partial sums live in
+// registers; block partials meet in shared memory, then one global atomic per channel per block.
+// ------------------------------------------------------------------------------------------------
+struct V8 { float v[8]; };
+
+__device__ __forceinline__ V8 ld8(const void* base, int dtype, int64_t idx) {
+  V8 r;
+  if (dtype == ICF_F32) {
+    const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+    const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx + 4);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      r.v[2 * i] = __uint_as_float(w[i] << 16);
+      r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  return r;
+}
+__device__ __forceinline__ void st8(void* base, int dtype, int64_t idx, const V8& r) {
+  if (dtype == ICF_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+  } else {
+    uint4 u;
+    uint32_t* w = &u.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = u;
+  }
+}
+__device__ __forceinline__ V8 ldf8(const float* p) {   // 8 consecutive floats, 16-byte aligned
+  V8 r;
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+
+constexpr int VT = 256;          // threads per block of the vector kernels
+constexpr int VSM = 2048;        // channels a block can hold partial sums for
+
+// flush per-thread channel partials: shared-memory atomics, then one global atomic per channel per block
+template <int NS>
+__device__ __forceinline__ void flush_partials(float (*acc)[8], int cbase_block, int c0, int C, int span,
+                                               float* const* dst, float* sm) {
+  for (int i = threadIdx.x; i < NS * span; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  if (c0 < C) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sm[s * span + (c0 - cbase_block) + j], acc[s][j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NS * span; i += blockDim.x) {
+    const int s = i / span, c = cbase_block + (i - s * span);
+    if (c < C && dst[s]) atomicAdd(dst[s] + c, sm[i]);
+  }
+}
+
+// thread -> (channel group, first pixel, pixel stride).  cg = C/8 groups; a block covers min(cg, VT) groups.
+struct VMap { int c0, cbase_block, span; int64_t pix0, pstride; };
+__device__ __forceinline__ VMap vmap(int C, int64_t pixels) {
+  const int cg = C >> 3;
+  const int gpb = cg < VT ? cg : VT;                  // channel groups per block
+  const int cblocks = (cg + gpb - 1) / gpb;           // blocks along channels
+  const int cb = blockIdx.x % cblocks;
+  const int64_t pb = blockIdx.x / cblocks, npb = gridDim.x / cblocks;
+  const int rows = VT / gpb;                          // pixel rows per block pass
+  VMap m;
+  m.cbase_block = cb * gpb * 8;
+  m.span = gpb * 8;
+  m.c0 = m.cbase_block + (threadIdx.x % gpb) * 8;
+  m.pix0 = pb * rows + threadIdx.x / gpb;
+  m.pstride = npb * rows;
+  if ((int)threadIdx.x / gpb >= rows) m.c0 = 1 << 30;   // leftover threads when gpb does not divide the block
+  return m;
+}
+inline int vgrid(int C, int64_t pixels) {
+  const int cg = C >> 3;
+  const int gpb = cg < VT ? cg : VT;
+  const int cblocks = (cg + gpb - 1) / gpb;
+  const int rows = VT / gpb;
+  int64_t pblocks = (pixels + rows - 1) / rows;
+  const int64_t cap = (148 * 8 + cblocks - 1) / cblocks;
+  if (pblocks > cap) pblocks = cap;
+  if (pblocks < 1) pblocks = 1;
+  return (int)(pblocks * cblocks);
+}
+
+__global__ void __launch_bounds__(VT) scale_shift_mask_v8(const void* y, int ydt, int ypitch, void* u, int udt, int upitch,
+                                                          int64_t pixels, int pps, int C, const float* scale,
+                                                          const float* shift, const float* mask, int mpitch) {
+  const VMap m = vmap(C, pixels);
+  if (m.c0 >= C) return;
+  V8 sc, sh;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc.v[j] = scale ? scale[m.c0 + j] : 1.f; sh.v[j] = (scale && shift) ? shift[m.c0 + j] : 0.f; }
+  for (int64_t pix = m.pix0; pix < pixels; pix += m.pstride) {
+    V8 v = ld8(y, ydt, pix * ypitch + m.c0);
+    if (scale) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.v[j] = fmaf(v.v[j], sc.v[j], sh.v[j]);
+    }
+    if (mask) {
+      const V8 mk = ldf8(mask + (pix / pps) * mpitch + m.c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.v[j] *= mk.v[j];
+    }
+    st8(u, udt, pix * upitch + m.c0, v);
+  }
+}
+
+__global__ void __launch_bounds__(VT) bn_bwd_reduce_v8(const void* dU, int ddt, int dpitch, const void* y, int ydt, int ypitch,
+                                                       int64_t pixels, int pps, int C, const float* mask, int mpitch,
+                                                       const float* mean, const float* invstd, float* sums) {
+  __shared__ float sm[2 * VSM];
+  const VMap m = vmap(C, pixels);
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  if (m.c0 < C) {
+    const V8 mu = ldf8(mean + m.c0), is = ldf8(invstd + m.c0);
+    for (int64_t pix = m.pix0; pix < pixels; pix += m.pstride) {
+      V8 g = ld8(dU, ddt, pix * dpitch + m.c0);
+      const V8 yv = ld8(y, ydt, pix * ypitch + m.c0);
+      if (mask) {
+        const V8 mk = ldf8(mask + (pix / pps) * mpitch + m.c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.v[j] *= mk.v[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += g.v[j];
+        acc[1][j] = fmaf(g.v[j], (yv.v[j] - mu.v[j]) * is.v[j], acc[1][j]);
+      }
+    }
+  }
+  float* dst[2] = {sums, sums + C};
+  flush_partials<2>(acc, m.cbase_block, m.c0, C, m.span, dst, sm);
+}
+
+__global__ void __launch_bounds__(VT) col_stats_v8(const void* y, int ydt, int ypitch, int64_t pixels, int C, float* stats) {
+  __shared__ float sm[2 * VSM];
+  const VMap m = vmap(C, pixels);
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  if (m.c0 < C) {
+    for (int64_t pix = m.pix0; pix < pixels; pix += m.pstride) {
+      const V8 v = ld8(y, ydt, pix * ypitch + m.c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[0][j] += v.v[j]; acc[1][j] = fmaf(v.v[j], v.v[j], acc[1][j]); }
+    }
+  }
+  float* dst[2] = {stats, stats + C};
+  flush_partials<2>(acc, m.cbase_block, m.c0, C, m.span, dst, sm);
+}
+
+__global__ void __launch_bounds__(VT) act_backward_v8(const icf_actbwd_args a) {
+  __shared__ float sm[VSM];
+  const VMap m = vmap(a.C, a.pixels);
+  float acc[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+  if (m.c0 < a.C) {
+    const bool bn = a.bn_sums != nullptr;
+    V8 gs, m0, m1, mu, is;
+    if (bn) {
+      const float invM = 1.f / (float)a.pixels;
+      mu = ldf8(a.bn_mean + m.c0);
+      is = ldf8(a.bn_invstd + m.c0);
+      const V8 ga = ldf8(a.bn_gamma + m.c0), s0 = ldf8(a.bn_sums + m.c0), s1 = ldf8(a.bn_sums + a.C + m.c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { gs.v[j] = ga.v[j] * is.v[j]; m0.v[j] = s0.v[j] * invM; m1.v[j] = s1.v[j] * invM; }
+      if (m.pix0 == 0) {            // exactly one thread per channel group has pix0 == 0
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (a.bn_dgamma) a.bn_dgamma[m.c0 + j] += s1.v[j];
+          if (a.bn_dbeta) a.bn_dbeta[m.c0 + j] += s0.v[j];
+        }
+      }
+    }
+    for (int64_t pix = m.pix0; pix < a.pixels; pix += m.pstride) {
+      const int64_t n = pix / a.pixels_per_sample;
+      V8 g = ld8(a.dOut, a.d_dtype, pix * a.d_pitch + m.c0);
+      const V8 yv = ld8(a.y, a.y_dtype, pix * a.y_pitch + m.c0);
+      if (bn) {
+        if (a.bn_mask) {
+          const V8 mk = ldf8(a.bn_mask + n * a.bn_mask_pitch + m.c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g.v[j] *= mk.v[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.v[j] = gs.v[j] * (g.v[j] - m0.v[j] - (yv.v[j] - mu.v[j]) * is.v[j] * m1.v[j]);
+      }
+      if (a.out_mask) {
+        const V8 mk = ldf8(a.out_mask + n * a.mask_pitch + m.c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.v[j] *= mk.v[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        g.v[j] *= icf::act_grad_from_output(yv.v[j], a.act, a.slope);
+        acc[0][j] += g.v[j];
+      }
+      st8(a.dPre, a.p_dtype, pix * a.p_pitch + m.c0, g);
+    }
+  }
+  if (a.dbias) {
+    float* dst[1] = {a.dbias};
+    flush_partials<1>(acc, m.cbase_block, m.c0, a.C, m.span, dst, sm);
+  }
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+// BatchNorm statistics of a stored tensor (used after a tensor-core conv, whose epilogue does not reduce columns)
+int icf_launch_col_stats(const void* y, int ydt, int ypitch, int64_t pixels, int C, float* stats, cudaStream_t st) {
+  if ((C & 7) || (ypitch & 7) || !al16(y)) { icf::set_error("col_stats: needs 8-channel aligned tensors"); return 1; }
+  col_stats_v8<<<vgrid(C, pixels), VT, 0, st>>>(y, ydt, ypitch, pixels, C, stats);
+  return icf::check_launch("col_stats_v8");
+}
+
+namespace {
+inline bool al32f(const void* p, int dt) { return (reinterpret_cast<uintptr_t>(p) & (dt == ICF_F32 ? 15 : 15)) == 0; }
+
 // ------------------------------------------------------------------------------------------------
 // BCE with logits (mean) forward+backward; sigmoid mean (phase-D scores). Single block.
 // ------------------------------------------------------------------------------------------------
@@ -391,6 +635,31 @@ __global__ void unpack_kernel(const float* __restrict__ src, float* dst, const i
   }
 }
 
+__global__ void pack4_kernel(const float* __restrict__ src, void* dst, int ddt, const icf_perm4 p) {
+  const int64_t total = p.d0 * p.d1 * p.row_pitch;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t col = i % p.row_pitch, row = i / p.row_pitch;
+    const int64_t i1 = row % p.d1, i0 = row / p.d1;
+    const int64_t i2 = col / p.d3_pad, i3 = col - i2 * p.d3_pad;
+    float v = 0.f;
+    if (i2 < p.d2 && i3 < p.d3) v = src[i0 * p.s0 + i1 * p.s1 + i2 * p.s2 + i3 * p.s3];
+    icf::st_any(dst, ddt, i, v);
+  }
+}
+
+__global__ void unpack4_kernel(const float* __restrict__ src, float* dst, const icf_perm4 p) {
+  const int64_t total = p.d0 * p.d1 * p.d2 * p.d3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int64_t i3 = t % p.d3; t /= p.d3;
+    const int64_t i2 = t % p.d2; t /= p.d2;
+    const int64_t i1 = t % p.d1, i0 = t / p.d1;
+    dst[i0 * p.s0 + i1 * p.s1 + i2 * p.s2 + i3 * p.s3] = src[(i0 * p.d1 + i1) * p.row_pitch + i2 * p.d3_pad + i3];
+  }
+}
+
 __global__ void cast_kernel(const void* src, int sdt, void* dst, int ddt, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     icf::st_any(dst, ddt, i, icf::ld_any(src, sdt, i));
@@ -435,7 +704,7 @@ int icf_image_features_fwd(const icf_imgfeat_args* a, void* stream) {
                   1 + a->n_emb + a->n_cont <= a->feat_pitch,
               "icf_image_features_fwd: %d emb + %d cont planes do not fit pitch %d", a->n_emb, a->n_cont,
               a->feat_pitch);
-  const int64_t total = (int64_t)a->N * a->H * a->W;
+  const int64_t total = (int64_t)a->N * (a->H + 2 * a->pad) * (a->W + 2 * a->pad);
   if (total == 0) return 0;
   imgfeat_fwd_kernel<<<icf::cdiv(total, EW_THREADS), EW_THREADS, 0, icf::as_stream(stream)>>>(*a);
   return icf::check_launch("imgfeat_fwd");
@@ -497,6 +766,12 @@ int icf_scale_shift_mask(const void* y, int32_t y_dtype, int32_t y_pitch, void* 
                          void* stream) {
   ICF_REQUIRE(y && u && C > 0 && pixels_per_sample > 0, "icf_scale_shift_mask: bad arguments");
   if (pixels == 0) return 0;
+  if ((C & 7) == 0 && (y_pitch & 7) == 0 && (u_pitch & 7) == 0 && al16(y) && al16(u) && (!mask || ((mask_pitch & 3) == 0 && al16(mask))) &&
+      (!scale || al16(scale)) && (!shift || al16(shift))) {
+    scale_shift_mask_v8<<<vgrid(C, pixels), VT, 0, icf::as_stream(stream)>>>(y, y_dtype, y_pitch, u, u_dtype, u_pitch, pixels,
+                                                                             pixels_per_sample, C, scale, shift, mask, mask_pitch);
+    return icf::check_launch("scale_shift_mask_v8");
+  }
   scale_shift_mask_kernel<<<ew_grid(pixels * C, 4), EW_THREADS, 0, icf::as_stream(stream)>>>(
       y, y_dtype, y_pitch, u, u_dtype, u_pitch, pixels, pixels_per_sample, C, scale, shift, mask, mask_pitch);
   return icf::check_launch("scale_shift_mask");
@@ -508,6 +783,13 @@ int icf_bn_bwd_reduce(const void* dU, int32_t d_dtype, int32_t d_pitch, const vo
                       void* stream) {
   ICF_REQUIRE(dU && y && save_mean && save_invstd && sums && C > 0, "icf_bn_bwd_reduce: bad arguments");
   if (pixels == 0) return 0;
+  if ((C & 7) == 0 && (d_pitch & 7) == 0 && (y_pitch & 7) == 0 && al16(dU) && al16(y) && al16(save_mean) && al16(save_invstd) &&
+      (!mask || ((mask_pitch & 3) == 0 && al16(mask)))) {
+    bn_bwd_reduce_v8<<<vgrid(C, pixels), VT, 0, icf::as_stream(stream)>>>(dU, d_dtype, d_pitch, y, y_dtype, y_pitch, pixels,
+                                                                          pixels_per_sample, C, mask, mask_pitch, save_mean,
+                                                                          save_invstd, sums);
+    return icf::check_launch("bn_bwd_reduce_v8");
+  }
   const int groups = icf::cdiv(C, 32);
   dim3 grid(groups, pixel_slabs(pixels, groups));
   bn_bwd_reduce_kernel<<<grid, 256, 0, icf::as_stream(stream)>>>(dU, d_dtype, d_pitch, y, y_dtype, y_pitch,
@@ -522,6 +804,17 @@ int icf_act_backward(const icf_actbwd_args* a, void* stream) {
   if (a->bn_sums)
     ICF_REQUIRE(a->bn_gamma && a->bn_mean && a->bn_invstd, "icf_act_backward: incomplete BatchNorm state");
   if (a->pixels == 0) return 0;
+  {
+    bool ok = (a->C & 7) == 0 && (a->d_pitch & 7) == 0 && (a->y_pitch & 7) == 0 && (a->p_pitch & 7) == 0 && al16(a->dOut) &&
+              al16(a->y) && al16(a->dPre) && a->bias_mod == 0;
+    if (a->out_mask) ok = ok && (a->mask_pitch & 3) == 0 && al16(a->out_mask);
+    if (a->bn_sums) ok = ok && al16(a->bn_sums) && al16(a->bn_gamma) && al16(a->bn_mean) && al16(a->bn_invstd) && (a->C & 3) == 0 &&
+                      (!a->bn_mask || ((a->bn_mask_pitch & 3) == 0 && al16(a->bn_mask)));
+    if (ok) {
+      act_backward_v8<<<vgrid(a->C, a->pixels), VT, 0, icf::as_stream(stream)>>>(*a);
+      return icf::check_launch("act_backward_v8");
+    }
+  }
   const int groups = icf::cdiv(a->C, 32);
   dim3 grid(groups, pixel_slabs(a->pixels, groups));
   act_backward_kernel<<<grid, 256, 0, icf::as_stream(stream)>>>(*a);
@@ -569,6 +862,22 @@ int icf_unpack(const float* src_packed, float* dst, const icf_perm* p, int32_t a
   if (total == 0) return 0;
   unpack_kernel<<<ew_grid(total), EW_THREADS, 0, icf::as_stream(stream)>>>(src_packed, dst, *p, atomic_add);
   return icf::check_launch("unpack");
+}
+
+int icf_pack4(const float* src, void* dst, int32_t dst_dtype, const icf_perm4* p, void* stream) {
+  ICF_REQUIRE(src && dst && p && p->d3_pad >= p->d3 && p->row_pitch >= p->d2 * p->d3_pad, "icf_pack4: bad arguments");
+  const int64_t total = p->d0 * p->d1 * p->row_pitch;
+  if (total == 0) return 0;
+  pack4_kernel<<<ew_grid(total), EW_THREADS, 0, icf::as_stream(stream)>>>(src, dst, dst_dtype, *p);
+  return icf::check_launch("pack4");
+}
+
+int icf_unpack4(const float* src_packed, float* dst, const icf_perm4* p, void* stream) {
+  ICF_REQUIRE(src_packed && dst && p, "icf_unpack4: bad arguments");
+  const int64_t total = p->d0 * p->d1 * p->d2 * p->d3;
+  if (total == 0) return 0;
+  unpack4_kernel<<<ew_grid(total), EW_THREADS, 0, icf::as_stream(stream)>>>(src_packed, dst, *p);
+  return icf::check_launch("unpack4");
 }
 
 int icf_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream) {

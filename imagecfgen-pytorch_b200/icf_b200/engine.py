@@ -52,9 +52,10 @@ class Act:
 class LayerExec:
     """One conv-shaped contraction with its packed operands (Conv2d / ConvTranspose2d / Linear+Unflatten)."""
 
-    def __init__(self, spec: L, hin: int, win: int, code: int, device):
+    def __init__(self, spec: L, hin: int, win: int, code: int, device, fold: bool = False):
         self.spec, self.code, self.device = spec, code, device
         self.Hin, self.Win = hin, win
+        self.fold = 0
         if spec.kind == "conv":
             self.form, self.taps_r = ops.GATHER, spec.k
             self.P, self.Q = conv_out(hin, spec.k, spec.stride, spec.pad), conv_out(win, spec.k, spec.stride, spec.pad)
@@ -110,11 +111,24 @@ class LayerExec:
             self.perm_g = ops.make_perm(hw, cu, C_, C_, hw * C_, 1)              # dw packed [hw*cu][C]
             self.perm_bias = ops.make_perm(1, hw, cu, 0, 1, hw)
         self.wgrad_elems = self.Kout * self.taps * self.Cin
+        # folded form of a small-channel first conv (bf16 tensor-core path): the S filter columns become part of
+        # the channel dimension of a pre-padded 8-channel input, cutting the K loop from R*S taps to R rows
+        if fold and spec.kind == "conv" and code == BF16 and pad8(self.Cin) == 8 and self.S * 8 <= 64 and self.S > 1:
+            self.fold = self.S
+            self.fold_pitch = 64
+            self.w_fold = torch.zeros(K_ * self.R * self.fold_pitch, dtype=dt, device=device)
+            self.perm_fold = ops.make_perm4(K_, self.R, self.S, C_, C_ * T, self.S, 1, T, 8, self.fold_pitch)
+            self.perm_fold_g = ops.make_perm4(K_, self.R, self.S, C_, C_ * T, self.S, 1, T, 8, self.S * 8)
+            self.wgrad_elems = K_ * self.R * self.S * 8
+        self.alg_flops_img = 2.0 * self.Cin * self.Kout * ops.valid_taps(self.form, hin, self.P, self.R, self.stride, self.pad) \
+            * ops.valid_taps(self.form, win, self.Q, self.S, self.stride, self.pad)
 
     # ---- operands -------------------------------------------------------------------------------
     def repack(self, weight: torch.Tensor, bias: torch.Tensor):
         ops.pack(weight.data_ptr(), self.w_fwd.data_ptr(), self.code, self.perm_f)
         ops.pack(weight.data_ptr(), self.w_bwd.data_ptr(), self.code, self.perm_b)
+        if self.fold:
+            ops.pack4(weight.data_ptr(), self.w_fold.data_ptr(), self.code, self.perm_fold)
         if self.perm_bias is None:
             ops.cast(bias.data_ptr(), F32, self.bias.data_ptr(), F32, self.Kout)
         else:
@@ -123,6 +137,13 @@ class LayerExec:
     # ---- launches -------------------------------------------------------------------------------
     def forward(self, N, x: Act, y: Act, mask=None, mask_pitch=0, stats=None, out_f32=False):
         sp = self.spec
+        if self.fold:      # x is the pre-padded [N][Hin+2p][Win+2p][8] feature tensor
+            ops.conv_forward(self.code, self.form, N, self.Hin + 2 * self.pad, self.Win + 2 * self.pad,
+                             self.fold * x.pitch, x.pitch, self.P, self.Q, self.Kout, y.pitch, self.R, 1, self.stride, 0,
+                             x.ptr, self.w_fold.data_ptr(), self.Kout, self.fold_pitch, y.ptr, bias=self.bias.data_ptr(),
+                             act=sp.act, slope=sp.slope, out_f32=out_f32, mask=mask, mask_pitch=mask_pitch, stats=stats,
+                             win=self.fold, alg_flops=self.alg_flops_img * N)
+            return
         ops.conv_forward(self.code, self.form, N, self.Hin, self.Win, self.Cin, x.pitch,
                          self.P, self.Q, self.Kout, y.pitch if sp.kind != "linear" else y.pitch * self.Hout * self.Wout,
                          self.R, self.S, self.stride, self.pad, x.ptr, self.w_fwd.data_ptr(), self.Kout,
@@ -142,6 +163,12 @@ class LayerExec:
         """gw (checkpoint layout, fp32) = weight gradient; ``scratch`` holds the packed fp32 accumulator."""
         n = self.wgrad_elems
         ops.fill_f32(scratch.data_ptr(), 0.0, n)
+        if self.fold:
+            ops.conv_wgrad(self.code, N, self.P, self.Q, self.Kout, dpre.pitch, self.Hin + 2 * self.pad,
+                           self.Win + 2 * self.pad, self.fold * x.pitch, x.pitch, self.R, 1, self.stride, 0, dpre.ptr,
+                           x.ptr, scratch.data_ptr(), win=self.fold, alg_flops=self.alg_flops_img * N)
+            ops.unpack4(scratch.data_ptr(), gw.data_ptr(), self.perm_fold_g)
+            return
         lin = self.spec.kind == "linear"
         dp_pitch = dpre.pitch * self.Hout * self.Wout if lin else dpre.pitch
         if self.spec.kind == "convT":     # small = X (A = Cin), big = dY (B = Cout)
@@ -177,11 +204,11 @@ def draw_masks(fam: Family, n: int, device) -> List[torch.Tensor]:
 
 
 class Tower:
-    def __init__(self, specs, hin, win, code, device):
+    def __init__(self, specs, hin, win, code, device, fold_first=False):
         self.layers: List[LayerExec] = []
         h, w = hin, win
-        for s in specs:
-            le = LayerExec(s, h, w, code, device)
+        for i, s in enumerate(specs):
+            le = LayerExec(s, h, w, code, device, fold=(fold_first and i == 0))
             self.layers.append(le)
             h, w = le.Hout, le.Wout
         self.Hout, self.Wout = h, w
@@ -203,13 +230,13 @@ class NetExec:
         self.n_emb, self.n_cont = len(fam.cat_attrs), len(fam.cont_attrs)
         self.feat_ch = 1 + self.n_emb + self.n_cont
         if role == "E":
-            self.towers = {"E": Tower(fam.E, H, W, code, device)}
+            self.towers = {"E": Tower(fam.E, H, W, code, device, fold_first=True)}
         elif role == "G":
             self.towers = {"G": Tower(fam.G, 1, 1, code, device)}
             self.lat_dim = fam.latent + 256 * self.n_emb + self.n_cont
             assert self.lat_dim == fam.G[0].cin, (self.lat_dim, fam.G[0].cin)
         else:
-            self.towers = {"Dx": Tower(fam.Dx, H, W, code, device), "Dz": Tower(fam.Dz, 1, 1, code, device),
+            self.towers = {"Dx": Tower(fam.Dx, H, W, code, device, fold_first=True), "Dz": Tower(fam.Dz, 1, 1, code, device),
                            "Dxz": Tower(fam.Dxz, 1, 1, code, device)}
             self.sites = mask_sites(fam)
         self._versions = None
@@ -406,12 +433,18 @@ class NetExec:
         cats, conts = self._attr_inputs(c, N)
         idx = [ops.argmax_rows(t.detach()) for t in cats]
         tables = [ts[a[self.emb_key]] for a in self.fam.cat_attrs]
-        feat = Act(torch.empty((N * self.H * self.W, pad8(self.feat_ch)), dtype=self.dt, device=self.device),
-                   self.feat_ch)
+        first = self.towers["E" if self.role == "E" else "Dx"].layers[0]
+        fpad = first.pad if first.fold else 0            # folded first conv reads a zero-bordered tensor
+        Hp, Wp = self.H + 2 * fpad, self.W + 2 * fpad
+        rows = N * Hp * Wp
+        feat = Act(torch.empty((rows + (Wp if first.fold else 0), pad8(self.feat_ch)), dtype=self.dt,
+                               device=self.device), self.feat_ch)
+        if first.fold:
+            feat.t[rows:].zero_()                          # slack the folded rows of the last pixels run into
         ops.image_features(self.code, N, self.H, self.W, feat.pitch, x_ptr, x_code, x_pitch,
                            [t.data_ptr() for t in tables], [t.data_ptr() for t in idx],
                            [t.data_ptr() for t in conts], ops.ptr(mask), mask.shape[1] if mask is not None else 0,
-                           feat.ptr)
+                           feat.ptr, pad=fpad)
         return feat, {"idx": idx, "conts": conts, "mask": mask}
 
     def _image_feats_bwd(self, N, fstate, dfeat: Act, grads):

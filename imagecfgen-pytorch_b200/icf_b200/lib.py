@@ -25,7 +25,7 @@ class ConvArgs(C.Structure):
                 ("P", _i32), ("Q", _i32), ("K", _i32), ("out_pitch", _i32),
                 ("R", _i32), ("S", _i32), ("stride", _i32), ("pad", _i32),
                 ("w_rows", _i32), ("w_pitch", _i32), ("act", _i32), ("slope", _f32), ("out_f32", _i32),
-                ("mask_pitch", _i32), ("accumulate", _i32),
+                ("mask_pitch", _i32), ("accumulate", _i32), ("win", _i32),
                 ("src", _vp), ("w", _vp), ("bias", _vp), ("dst", _vp), ("out_mask", _vp), ("stats", _vp)]
 
 
@@ -34,7 +34,7 @@ class WgradArgs(C.Structure):
                 ("P", _i32), ("Q", _i32), ("A", _i32), ("a_pitch", _i32),
                 ("H", _i32), ("W", _i32), ("B", _i32), ("b_pitch", _i32),
                 ("R", _i32), ("S", _i32), ("stride", _i32), ("pad", _i32),
-                ("small_t", _vp), ("big_t", _vp), ("dw", _vp)]
+                ("small_t", _vp), ("big_t", _vp), ("dw", _vp), ("win", _i32)]
 
 
 class Perm(C.Structure):
@@ -42,10 +42,15 @@ class Perm(C.Structure):
                 ("d2_pad", _i64), ("d0_pad", _i64)]
 
 
+class Perm4(C.Structure):
+    _fields_ = [("d0", _i64), ("d1", _i64), ("d2", _i64), ("d3", _i64), ("s0", _i64), ("s1", _i64), ("s2", _i64),
+                ("s3", _i64), ("d3_pad", _i64), ("row_pitch", _i64)]
+
+
 class ImgFeatArgs(C.Structure):
     _fields_ = [("dtype", _i32), ("N", _i32), ("H", _i32), ("W", _i32), ("feat_pitch", _i32),
                 ("x_dtype", _i32), ("x_pitch", _i32), ("n_emb", _i32), ("n_cont", _i32),
-                ("mask_pitch", _i32),
+                ("mask_pitch", _i32), ("pad", _i32),
                 ("x", _vp), ("emb_table", _vp * MAX_PLANES), ("emb_index", _vp * MAX_PLANES),
                 ("cont", _vp * MAX_PLANES), ("mask", _vp), ("feat", _vp), ("dfeat", _vp),
                 ("demb_table", _vp * MAX_PLANES)]
@@ -81,6 +86,8 @@ _SIGS = {
     "icf_conv_wgrad": (_i32, [C.POINTER(WgradArgs), _vp]),
     "icf_pack": (_i32, [_vp, _vp, _i32, C.POINTER(Perm), _vp]),
     "icf_unpack": (_i32, [_vp, _vp, C.POINTER(Perm), _i32, _vp]),
+    "icf_pack4": (_i32, [_vp, _vp, _i32, C.POINTER(Perm4), _vp]),
+    "icf_unpack4": (_i32, [_vp, _vp, C.POINTER(Perm4), _vp]),
     "icf_argmax_rows": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "icf_image_features_fwd": (_i32, [C.POINTER(ImgFeatArgs), _vp]),
     "icf_image_features_bwd": (_i32, [C.POINTER(ImgFeatArgs), _vp]),

@@ -77,29 +77,33 @@ def valid_taps(form, H, P, R, stride, pad):
 
 def conv_forward(dtype, form, N, H, W, Cc, in_pitch, P, Q, K, out_pitch, R, S, stride, pad,
                  src, w, w_rows, w_pitch, dst, bias=None, act="none", slope=0.0, out_f32=False,
-                 mask=None, mask_pitch=0, stats=None, accumulate=False):
+                 mask=None, mask_pitch=0, stats=None, accumulate=False, win=0, alg_flops=None):
     """src/w/dst/bias/mask/stats are raw addresses (ints) or None."""
     a = _l.ConvArgs(dtype, form, N, H, W, Cc, in_pitch, P, Q, K, out_pitch, R, S, stride, pad,
                     w_rows, w_pitch, ACT[act], slope, 1 if out_f32 else 0, mask_pitch,
-                    1 if accumulate else 0, src, w, bias, dst, mask, stats)
+                    1 if accumulate else 0, win, src, w, bias, dst, mask, stats)
     fl = nb = 0.0
     det = ""
     if PROFILE is not None:
         es = 4 if dtype == F32 else 2
         fl = 2.0 * N * Cc * K * valid_taps(form, H, P, R, stride, pad) * valid_taps(form, W, Q, S, stride, pad)
         nb = float(es) * (N * (H * W * Cc + P * Q * K) + K * Cc * R * S)
-        det = f"{'gather' if form == GATHER else 'transp'} {Cc}x{H}x{W}->{K}x{P}x{Q} k{R}s{stride}p{pad}"
+        if alg_flops is not None:
+            fl = alg_flops
+        det = f"{'gather' if form == GATHER else 'transp'} {Cc}x{H}x{W}->{K}x{P}x{Q} k{R}s{stride}p{pad}" + (f" win{win}" if win > 1 else "")
     _launch("icf_conv_forward", _l.load().icf_conv_forward, C.byref(a), flops=fl, nbytes=nb, detail=det)
 
 
-def conv_wgrad(dtype, N, P, Q, A, a_pitch, H, W, B, b_pitch, R, S, stride, pad, small, big, dw):
-    a = _l.WgradArgs(dtype, N, P, Q, A, a_pitch, H, W, B, b_pitch, R, S, stride, pad, small, big, dw)
+def conv_wgrad(dtype, N, P, Q, A, a_pitch, H, W, B, b_pitch, R, S, stride, pad, small, big, dw, win=0, alg_flops=None):
+    a = _l.WgradArgs(dtype, N, P, Q, A, a_pitch, H, W, B, b_pitch, R, S, stride, pad, small, big, dw, win)
     fl = nb = 0.0
     if PROFILE is not None:
         es = 4 if dtype == F32 else 2
         fl = 2.0 * N * A * B * valid_taps(GATHER, H, P, R, stride, pad) * valid_taps(GATHER, W, Q, S, stride, pad)
         nb = float(es) * N * (H * W * B + P * Q * A) + 4.0 * A * B * R * S
-    det = f"wgrad A{A}x{P}x{Q} B{B}x{H}x{W} k{R}s{stride}p{pad}" if PROFILE is not None else ""
+    if alg_flops is not None:
+        fl = alg_flops
+    det = (f"wgrad A{A}x{P}x{Q} B{B}x{H}x{W} k{R}s{stride}p{pad}" + (f" win{win}" if win > 1 else "")) if PROFILE is not None else ""
     _launch("icf_conv_wgrad", _l.load().icf_conv_wgrad, C.byref(a), flops=fl, nbytes=nb, detail=det)
 
 
@@ -109,6 +113,18 @@ def make_perm(d0, d1, d2, s0, s1, s2, d2_pad=None, d0_pad=None):
 
 def pack(src, dst, dst_dtype, perm):
     _launch("icf_pack", _l.load().icf_pack, src, dst, dst_dtype, C.byref(perm))
+
+
+def make_perm4(d0, d1, d2, d3, s0, s1, s2, s3, d3_pad, row_pitch):
+    return _l.Perm4(d0, d1, d2, d3, s0, s1, s2, s3, d3_pad, row_pitch)
+
+
+def pack4(src, dst, dst_dtype, perm):
+    _launch("icf_pack4", _l.load().icf_pack4, src, dst, dst_dtype, C.byref(perm))
+
+
+def unpack4(src_packed, dst, perm):
+    _launch("icf_unpack4", _l.load().icf_unpack4, src_packed, dst, C.byref(perm))
 
 
 def unpack(src_packed, dst, perm, atomic_add=False):
@@ -138,10 +154,11 @@ def _vp_array(ptrs):
 
 
 def image_features(dtype, N, H, W, feat_pitch, x, x_dtype, x_pitch, tables, indices, conts, mask, mask_pitch,
-                   feat, dfeat=None, dtables=None, backward=False):
+                   feat, dfeat=None, dtables=None, backward=False, pad=0):
     a = _l.ImgFeatArgs()
     a.dtype, a.N, a.H, a.W, a.feat_pitch = dtype, N, H, W, feat_pitch
     a.x_dtype, a.x_pitch, a.n_emb, a.n_cont, a.mask_pitch = x_dtype, x_pitch, len(tables), len(conts), mask_pitch
+    a.pad = pad
     a.x = x
     a.emb_table = _vp_array(tables)
     a.emb_index = _vp_array(indices)

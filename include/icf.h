@@ -62,6 +62,10 @@ typedef struct icf_conv_args {
   int32_t out_f32;               /* 1: dst elements are float even when dtype == ICF_BF16 */
   int32_t mask_pitch;            /* row pitch of out_mask */
   int32_t accumulate;            /* 1: dst += result (f32 dst only; used by split dgrad) */
+  int32_t win;                   /* >1 (tensor-core gather form only): the S filter columns are folded into the
+                                    channel dimension — the operand row of (pixel, filter row r) is the contiguous
+                                    run of win*in_pitch elements starting at that pixel; pass S = 1, C = win*in_pitch
+                                    and w packed [rows][R][w_pitch].  Used for the small-channel first layers. */
   const void* src;
   const void* w;                 /* packed [w_rows][R*S][w_pitch], channels contiguous */
   const float* bias;             /* [K] or NULL */
@@ -83,6 +87,7 @@ typedef struct icf_wgrad_args {
   const void* small_t;
   const void* big_t;
   float* dw;                     /* [A][R*S][B] fp32, caller zeroes */
+  int32_t win;                   /* >1: as in icf_conv_args — big's row is win*b_pitch contiguous elements; S = 1 */
 } icf_wgrad_args;
 int icf_conv_wgrad(const icf_wgrad_args* a, void* stream);
 
@@ -101,6 +106,16 @@ typedef struct icf_perm {
 } icf_perm;
 int icf_pack(const float* src, void* dst, int32_t dst_dtype, const icf_perm* p, void* stream);
 int icf_unpack(const float* src_packed, float* dst, const icf_perm* p, int32_t atomic_add, void* stream);
+/* 4-index variant for the folded ("win") first-layer operands:
+ *   packed[(i0*d1 + i1)*row_pitch + i2*d3_pad + i3]  <->  ref[i0*s0 + i1*s1 + i2*s2 + i3*s3]   (zero padding) */
+typedef struct icf_perm4 {
+  int64_t d0, d1, d2, d3;
+  int64_t s0, s1, s2, s3;
+  int64_t d3_pad;                /* >= d3 */
+  int64_t row_pitch;             /* >= d2*d3_pad */
+} icf_perm4;
+int icf_pack4(const float* src, void* dst, int32_t dst_dtype, const icf_perm4* p, void* stream);
+int icf_unpack4(const float* src_packed, float* dst, const icf_perm4* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Attribute / latent feature assembly (mnist.py:47-55,77-85; audio_mnist.py:204-210,250-256).
@@ -118,6 +133,7 @@ typedef struct icf_imgfeat_args {
   int32_t x_pitch;               /* elements between consecutive pixels of x (1 for a plain image) */
   int32_t n_emb, n_cont;
   int32_t mask_pitch;
+  int32_t pad;                   /* fwd: feat is [N][H+2pad][W+2pad][feat_pitch] with a zero border (pre-padded conv input) */
   const void* x;                 /* [N][H][W][x_pitch], channel 0 is the image */
   const float* emb_table[ICF_MAX_PLANES];   /* [K_i][256] */
   const int32_t* emb_index[ICF_MAX_PLANES]; /* [N] */
