@@ -30,6 +30,7 @@ int check_launch(const char* what) {
 }
 
 static std::atomic<int> g_tc{-1};
+static thread_local int g_conv_path = -1;
 
 }  // namespace icf
 
@@ -48,6 +49,7 @@ int icf_tc_enabled(void) {
   return v;
 }
 void icf_set_tc_enabled(int on) { icf::g_tc.store(on ? 1 : 0); }
+int icf_last_conv_path(void) { return icf::g_conv_path; }
 
 static int validate_conv(const icf_conv_args* a) {
   ICF_REQUIRE(a, "icf_conv_forward: null args");
@@ -73,9 +75,15 @@ int icf_conv_forward(const icf_conv_args* a, void* stream) {
   if (a->N == 0) return 0;
   cudaStream_t st = icf::as_stream(stream);
   if (a->dtype == ICF_BF16 && icf_tc_enabled()) {
-    int r = icf_tc_conv_forward(a, st);
-    if (r >= 0) return r;
+    static const bool ws_on = []() { const char* e = getenv("ICF_DISABLE_WS"); return !(e && e[0] && e[0] != '0'); }();
+    if (ws_on) {
+      int r = icf_ws_conv_forward(a, st);     // weight-stationary row-streaming kernel (small weight slabs)
+      if (r >= 0) { icf::g_conv_path = ICF_PATH_WS; return r; }
+    }
+    int r = icf_tc_conv_forward(a, st);       // per-tap implicit GEMM (large weights, GEMM-like layers)
+    if (r >= 0) { icf::g_conv_path = ICF_PATH_TC; return r; }
   }
+  icf::g_conv_path = ICF_PATH_SIMT;
   ICF_REQUIRE(a->win <= 1, "icf_conv_forward: the folded (win) form exists only on the tensor-core path");
   return icf_simt_conv_forward(a, st);
 }

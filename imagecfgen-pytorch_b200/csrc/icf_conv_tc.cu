@@ -12,16 +12,15 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
 // warps 2..5 = epilogue (TMEM -> registers -> bias/activation/Dropout2d mask -> global), one D row per thread.
-#include "icf_common.cuh"
-
-#include <cuda.h>
+#include "icf_epilogue.cuh"
 
 namespace {
+
+using namespace icf_tc;
 
 constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
 constexpr int MAX_CLASSES = 16, MAX_TAPS = 25;
 constexpr int NUM_THREADS = 192;
-constexpr long long SPIN_CYCLES = 4000000000LL;   // ~2 s: a wedged pipeline traps instead of hanging the GPU
 
 struct TapTable {
   int16_t ntaps[MAX_CLASSES];
@@ -48,118 +47,6 @@ struct TcParams {
   TapTable tt;
 };
 
-// ---- PTX wrappers --------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > SPIN_CYCLES) {
-      printf("icf conv_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-template <int COLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_result) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "n"(COLS)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int COLS>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// shared-memory matrix descriptor: K-major (or MN-major) tile, 128-byte swizzle, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
-  return d;
-}
-// instruction descriptor: D fp32, A/B bf16, M x N tile, operand majors (0 = K-major, 1 = MN-major)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
 // ------------------------------------------------------------------------------------------------
 // forward / dgrad kernel
 // ------------------------------------------------------------------------------------------------
@@ -175,6 +62,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);   // full[S], empty[S], tmem_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  float* sbias = reinterpret_cast<float*>(bars + 16);           // TILE_N floats, 128 B past the barriers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -262,6 +150,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
     // ===== epilogue: one D row (TMEM lane) per thread =====
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;
+    // bias tile -> shared memory (zero where absent / beyond K), visible to the four epilogue warps
+    for (int j = (int)threadIdx.x - 64; j < TILE_N; j += 128) sbias[j] = (p.bias && k0 + j < p.K) ? __ldg(p.bias + k0 + j) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     const int tij = p.ti * p.tj;
     const int tn_i = m / tij, rem = m - tn_i * tij;
     const int ti_i = rem / p.tj, tj_i = rem - ti_i * p.tj;
@@ -269,12 +160,15 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
     const bool valid = (tn_i < p.tn) && n < p.N && ii < Pi && jj < Qj;
     const int op = py + ii * p.ostep, oq = px + jj * p.ostep;
     const int64_t pix = valid ? ((int64_t)n * p.P + op) * p.Q + oq : 0;
-    const float* mrow = (p.mask && valid) ? p.mask + (int64_t)n * p.mask_pitch : nullptr;
+    const float* mrow = (p.mask && valid) ? p.mask + (int64_t)n * p.mask_pitch + k0 : nullptr;
+    const int esize = p.out_f32 ? 4 : 2;
+    uint8_t* orow = reinterpret_cast<uint8_t*>(p.dst) + (pix * p.out_pitch + k0) * esize;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
     for (int c0 = 0; c0 < TILE_N; c0 += 16) {
-      if (k0 + c0 >= p.K) break;     // uniform across the CTA
+      const int nv = p.K - (k0 + c0);
+      if (nv <= 0) break;            // uniform across the CTA
       uint32_t v[16];
       if (n_iters > 0) {
         tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, v);
@@ -284,39 +178,15 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
         for (int j = 0; j < 16; ++j) v[j] = 0u;
       }
       if (!valid) continue;
-      float f[16];
+      float mk[16];
+      if (mrow) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int k = k0 + c0 + j;
-        float x = __uint_as_float(v[j]);
-        if (k < p.K) {
-          if (p.bias) x += __ldg(p.bias + k);
-          x = icf::apply_act(x, p.act, p.slope);
-          if (mrow) x *= __ldg(mrow + k);
-        }
-        f[j] = x;
-      }
-      const int kbase = k0 + c0;
-      if (p.out_f32) {
-        float* o = reinterpret_cast<float*>(p.dst) + pix * p.out_pitch + kbase;
-        if (kbase + 16 <= p.K && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        } else {
-          for (int j = 0; j < 16 && kbase + j < p.K; ++j) o[j] = f[j];
-        }
+        for (int j = 0; j < 16; ++j) mk[j] = (j < nv) ? __ldg(mrow + c0 + j) : 0.f;
       } else {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dst) + pix * p.out_pitch + kbase;
-        if (kbase + 16 <= p.K && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-          uint4 a, b;
-          a.x = pack_bf16(f[0], f[1]); a.y = pack_bf16(f[2], f[3]); a.z = pack_bf16(f[4], f[5]); a.w = pack_bf16(f[6], f[7]);
-          b.x = pack_bf16(f[8], f[9]); b.y = pack_bf16(f[10], f[11]); b.z = pack_bf16(f[12], f[13]); b.w = pack_bf16(f[14], f[15]);
-          *reinterpret_cast<uint4*>(o) = a;
-          *reinterpret_cast<uint4*>(o + 8) = b;
-        } else {
-          for (int j = 0; j < 16 && kbase + j < p.K; ++j) o[j] = __float2bfloat16_rn(f[j]);
-        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) mk[j] = 1.f;
       }
+      epi16(v, sbias + c0, mk, p.act, p.slope, nv < 16 ? nv : 16, p.out_f32, orow + c0 * esize);
     }
   }
   tc_fence_before();
@@ -453,37 +323,9 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-// ---- host side ------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return reinterpret_cast<EncodeTiledFn>(f);
-  }();
-  return fn;
-}
-
-int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box, const cuuint32_t* estr) {
-  EncodeTiledFn fn = get_encode();
-  ICF_REQUIRE(fn, "tensor-core conv: cuTensorMapEncodeTiled is unavailable");
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  ICF_REQUIRE(r == CUDA_SUCCESS, "tensor-core conv: cuTensorMapEncodeTiled failed (%d)", (int)r);
-  return 0;
-}
-
 template <int TILE_N, int STAGES>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int64_t grid, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + TILE_N * BLOCK_K * 2) + 1024 + 256;
+  constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + TILE_N * BLOCK_K * 2) + 1024 + 256 + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<TILE_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,

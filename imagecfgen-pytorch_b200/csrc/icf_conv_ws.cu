@@ -1,0 +1,442 @@
+// Weight-stationary, row-streaming implicit-GEMM convolution for sm_100a (tcgen05.mma, TMEM accumulators, TMA).
+//
+// Serves the layers whose packed weights fit in shared memory (the small-channel first / last layers and the
+// per-parity-class slabs of the stride-2 transposed convolutions) — the layers that are HBM-bound on the roofline
+// and that an im2col-style kernel turns into L2-bound ones by fetching every activation once per filter tap.
+//
+//   * A persistent CTA owns one (parity class, 64-or-fewer output-channel tile): it loads that weight slab ONCE.
+//   * Its work items are "columns": XG adjacent output x positions of NG images (XG*NG = 128 = the MMA M).
+//     Operand rows are stored batch-innermost, [x][image][64 channels] in 128B-swizzled K-major form, so the
+//     operand of filter tap (dy, dx) is the same shared-memory tile shifted by dx*NG rows — a multiple of the
+//     1024-byte swizzle atom, i.e. a plain descriptor start-address offset.  Every source row is therefore
+//     fetched from L2 once (plus the x halo), not once per tap.
+//   * Source rows stream through a ring of slots in increasing y.  Row y feeds every output row i with
+//     i*sstep + dy == y, each accumulating in its own TMEM accumulator (a ring of n_acc); an output row retires
+//     to the epilogue warps as soon as its last source row has been issued, so TMEM -> bias/activation/Dropout2d
+//     -> global stores overlap the MMAs of the following rows.
+//   * Stride-2 gathers read each source row as two x-parity sub-rows (TMA element stride 2); transposed forms are
+//     unit-stride gathers per output-parity class (no zero insertion).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#include "icf_epilogue.cuh"
+
+#include <cstring>
+
+namespace {
+
+using namespace icf_tc;
+
+constexpr int WS_THREADS = 192;
+constexpr int WS_MAX_CLASSES = 4, WS_MAX_TAPS = 25, WS_MAX_SUBS = 2, WS_MAX_ACC = 16, WS_MAX_SLOTS = 8;
+constexpr int WS_SMEM_BUDGET = 220 * 1024;
+
+struct WsTap {
+  int16_t dy;        // source row = i*sstep + dy
+  int16_t widx;      // tap index r*S+s into the packed weights
+  uint32_t a_off;    // byte offset of this tap's operand inside a slot (sub-row + x shift)
+};
+
+struct WsClass {
+  int Pi, Qj, py, px;
+  int ntaps, ylo, yhi, dymax;
+  int x0[WS_MAX_SUBS];         // TMA x start = j0*sstep + x0[sub]
+  int tiles_x, cta_begin, cta_count;
+  WsTap taps[WS_MAX_TAPS];
+};
+
+struct WsParams {
+  int N, P, Q, K, out_pitch;
+  int sstep, ostep, n_classes;
+  int XG, NG, ng_shift;
+  int kchunks, kdepth_last, w_pitch;
+  int nsub, n_slots, n_acc, acc_shift;
+  int tiles_n, tiles_k;
+  uint32_t slot_bytes, sub_bytes, kc_bytes, slab_bytes, tmem_cols;
+  int act;
+  float slope;
+  int out_f32, mask_pitch;
+  const float* bias;
+  const float* mask;
+  void* dst;
+  WsClass cls[WS_MAX_CLASSES];
+};
+
+template <int TILE_N>
+__global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                             const __grid_constant__ CUtensorMap map_b,
+                                                             const __grid_constant__ WsParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wslab = smem;
+  uint8_t* slots = smem + p.slab_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slots + (size_t)p.n_slots * p.slot_bytes);
+  // barrier layout: slot_full[8] slot_empty[8] acc_full[16] acc_empty[16] w_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WS_MAX_SLOTS + 2 * WS_MAX_ACC + 1);
+  float* sbias = reinterpret_cast<float*>(bars + 64);          // TILE_N floats, 512 B past the barriers
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int cls = 0;
+  while (cls + 1 < p.n_classes && (int)blockIdx.x >= p.cls[cls].cta_begin + p.cls[cls].cta_count) ++cls;
+  const WsClass& cl = p.cls[cls];
+  const int local = (int)blockIdx.x - cl.cta_begin;
+  const int kt = local % p.tiles_k, r0 = local / p.tiles_k, rstep = cl.cta_count / p.tiles_k;
+  const int k0 = kt * TILE_N;
+  const int ncols = p.tiles_n * cl.tiles_x;
+
+  const uint32_t bar_base = smem_u32(bars);
+  auto slot_full = [&](int s) { return bar_base + 8u * s; };
+  auto slot_empty = [&](int s) { return bar_base + 8u * (WS_MAX_SLOTS + s); };
+  auto acc_full = [&](int a) { return bar_base + 8u * (2 * WS_MAX_SLOTS + a); };
+  auto acc_empty = [&](int a) { return bar_base + 8u * (2 * WS_MAX_SLOTS + WS_MAX_ACC + a); };
+  const uint32_t w_full = bar_base + 8u * (2 * WS_MAX_SLOTS + 2 * WS_MAX_ACC);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b);
+    for (int s = 0; s < WS_MAX_SLOTS; ++s) {
+      mbar_init(slot_full(s), 1);
+      mbar_init(slot_empty(s), 1);
+    }
+    for (int a = 0; a < WS_MAX_ACC; ++a) {
+      mbar_init(acc_full(a), 1);
+      mbar_init(acc_empty(a), 4);      // one arrival per epilogue warp
+    }
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_rt(smem_u32(tmem_slot), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t slab_addr = smem_u32(wslab), slots_addr = smem_u32(slots);
+  constexpr uint32_t W_BLOCK = TILE_N * 128;      // one (tap, K chunk) block of the weight slab
+
+  if (warp == 0) {
+    // ===== TMA producer: weight slab once, then the source rows of every column =====
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (uint32_t)(cl.ntaps * p.kchunks) * W_BLOCK);
+      for (int t = 0; t < cl.ntaps; ++t)
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_2d(slab_addr + (uint32_t)(t * p.kchunks + kc) * W_BLOCK, &map_b, w_full,
+                      cl.taps[t].widx * p.w_pitch + kc * 64, k0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int col = r0; col < ncols; col += rstep) {
+        const int jt = col % cl.tiles_x, nt = col / cl.tiles_x;
+        const int n0 = nt * p.NG, xs = jt * p.XG * p.sstep;
+        for (int y = cl.ylo; y <= cl.yhi; ++y) {
+          mbar_wait(slot_empty(s), ph ^ 1);
+          mbar_expect_tx(slot_full(s), p.slot_bytes);
+          const uint32_t base = slots_addr + (uint32_t)s * p.slot_bytes;
+          for (int sub = 0; sub < p.nsub; ++sub)
+            for (int kc = 0; kc < p.kchunks; ++kc)
+              tma_load_4d(base + sub * p.sub_bytes + kc * p.kc_bytes, &map_a, slot_full(s), kc * 64, n0,
+                          xs + cl.x0[sub], y);
+          if (++s == p.n_slots) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, TILE_N, 0, 0);
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      int s = 0;
+      uint32_t ph = 0;
+      int g_base = 0;                       // sequence number of this column's output row 0
+      for (int col = r0; col < ncols; col += rstep) {
+        uint32_t started = 0;               // bit per accumulator: output row has received its first MMA
+        int next_done = 0;
+        for (int y = cl.ylo; y <= cl.yhi; ++y) {
+          mbar_wait(slot_full(s), ph);
+          tc_fence_after();
+          const uint32_t base = slots_addr + (uint32_t)s * p.slot_bytes;
+          for (int t = 0; t < cl.ntaps; ++t) {
+            const int num = y - cl.taps[t].dy;
+            if (num < 0) continue;
+            const int i = p.sstep == 1 ? num : (num >> 1);
+            if (i * p.sstep != num || i >= cl.Pi) continue;
+            const int g = g_base + i, acc = g & (p.n_acc - 1);
+            const uint32_t bit = 1u << acc;
+            if (!(started & bit)) {
+              mbar_wait(acc_empty(acc), ((uint32_t)(g >> p.acc_shift) & 1u) ^ 1u);
+              tc_fence_after();
+            }
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * TILE_N;
+            const uint32_t a_addr = base + cl.taps[t].a_off, b_addr = slab_addr + (uint32_t)(t * p.kchunks) * W_BLOCK;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+              const int nk = (kc == p.kchunks - 1) ? p.kdepth_last : 4;
+              const uint64_t adesc = make_desc(a_addr + kc * p.kc_bytes, 16, 1024);
+              const uint64_t bdesc = make_desc(b_addr + kc * W_BLOCK, 16, 1024);
+              for (int k = 0; k < nk; ++k)
+                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((started & bit) || kc || k) ? 1u : 0u);
+            }
+            started |= bit;
+          }
+          umma_commit(slot_empty(s));
+          if (++s == p.n_slots) { s = 0; ph ^= 1; }
+          while (next_done < cl.Pi && (next_done * p.sstep + cl.dymax <= y || y == cl.yhi)) {
+            const int acc = (g_base + next_done) & (p.n_acc - 1);
+            umma_commit(acc_full(acc));     // host guarantees every output row has an in-bounds source row
+            started &= ~(1u << acc);
+            ++next_done;
+          }
+        }
+        g_base += cl.Pi;
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM lane m = x_local*NG + n_local =====
+    const int q4 = warp & 3;
+    const int m = q4 * 32 + lane;
+    const int x_local = m >> p.ng_shift, n_local = m & (p.NG - 1);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    // bias tile -> shared memory (zero where absent / beyond K), visible to the four epilogue warps
+    for (int j = (int)threadIdx.x - 64; j < TILE_N; j += 128) sbias[j] = (p.bias && k0 + j < p.K) ? __ldg(p.bias + k0 + j) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int esize = p.out_f32 ? 4 : 2;
+    int g = 0;
+    for (int col = r0; col < ncols; col += rstep) {
+      const int jt = col % cl.tiles_x, nt = col / cl.tiles_x;
+      const int n = nt * p.NG + n_local, jj = jt * p.XG + x_local;
+      const bool valid = n < p.N && jj < cl.Qj;
+      float mk[TILE_N];                      // Dropout2d mask row of this thread's image (1 where no mask)
+      if (p.mask && valid) {
+        const float* mrow = p.mask + (int64_t)n * p.mask_pitch + k0;
+#pragma unroll
+        for (int j = 0; j < TILE_N; ++j) mk[j] = (k0 + j < p.K) ? __ldg(mrow + j) : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < TILE_N; ++j) mk[j] = 1.f;
+      }
+      // destination of output row 0 of this thread's pixel column, channel k0
+      uint8_t* orow = reinterpret_cast<uint8_t*>(p.dst) +
+                      ((((int64_t)(valid ? n : 0) * p.P + cl.py) * p.Q + cl.px + (int64_t)(valid ? jj : 0) * p.ostep) * p.out_pitch + k0) * esize;
+      const int64_t row_step = (int64_t)p.ostep * p.Q * p.out_pitch * esize;
+      for (int i = 0; i < cl.Pi; ++i, ++g, orow += row_step) {
+        const int acc = g & (p.n_acc - 1);
+        mbar_wait(acc_full(acc), (uint32_t)(g >> p.acc_shift) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < TILE_N; c0 += 32) {
+          uint32_t va[16], vb[16];
+          tmem_ld16(lane_addr + (uint32_t)(acc * TILE_N + c0), va);
+          if (TILE_N > 16) tmem_ld16(lane_addr + (uint32_t)(acc * TILE_N + c0 + 16), vb);
+          tmem_ld_wait();
+          if (c0 + 32 >= TILE_N) {          // accumulator fully read: hand it back before the math and stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(acc));
+          }
+          if (valid) {
+            const int nv = p.K - (k0 + c0);
+            if (nv > 0)
+              epi16(va, sbias + c0, *reinterpret_cast<const float(*)[16]>(&mk[c0]), p.act, p.slope, nv < 16 ? nv : 16,
+                    p.out_f32, orow + c0 * esize);
+            if (TILE_N > 16 && nv > 16)
+              epi16(vb, sbias + c0 + 16, *reinterpret_cast<const float(*)[16]>(&mk[TILE_N > 16 ? c0 + 16 : 0]), p.act,
+                    p.slope, nv < 32 ? nv - 16 : 16, p.out_f32, orow + (c0 + 16) * esize);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc_rt(tmem_base, p.tmem_cols);
+}
+
+inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+inline int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+
+int sm_count() {
+  static int n = []() {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+    return v;
+  }();
+  return n;
+}
+
+template <int TILE_N>
+int launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, const WsParams& p, int grid, size_t smem, cudaStream_t st) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_ws_kernel<TILE_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ICF_REQUIRE(e == cudaSuccess, "row-streaming conv: cannot reserve %zu B of shared memory: %s", smem,
+                cudaGetErrorString(e));
+    configured = smem;
+  }
+  conv_ws_kernel<TILE_N><<<(unsigned)grid, WS_THREADS, smem, st>>>(ma, mb, p);
+  return icf::check_launch("conv_ws");
+}
+
+}  // namespace
+
+// returns 0 = launched, -1 = geometry outside this kernel's envelope (caller tries the next kernel), >0 = error
+int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
+  if (a->dtype != ICF_BF16 || a->accumulate) return -1;
+  if ((a->in_pitch & 7) || (a->w_pitch & 7)) return -1;
+  if (a->win > 1 && a->pad != 0) return -1;
+  if ((reinterpret_cast<uintptr_t>(a->src) & 15) || (reinterpret_cast<uintptr_t>(a->w) & 15)) return -1;
+  const bool gather = a->form == ICF_FORM_GATHER;
+  const int taps_all = a->R * a->S;
+  if (taps_all > WS_MAX_TAPS || a->stride > 2) return -1;
+
+  WsParams q;
+  memset(&q, 0, sizeof(q));
+  q.N = a->N; q.P = a->P; q.Q = a->Q; q.K = a->K; q.out_pitch = a->out_pitch;
+  q.sstep = gather ? a->stride : 1;
+  q.ostep = gather ? 1 : a->stride;
+  q.n_classes = q.ostep * q.ostep;
+  q.kchunks = icf::cdiv(a->C, 64);
+  q.kdepth_last = icf::cdiv(a->C - 64 * (q.kchunks - 1), 16);
+  q.w_pitch = a->w_pitch;
+  const int tile_n = a->K <= 16 ? 16 : (a->K <= 32 ? 32 : 64);
+  q.tiles_k = icf::cdiv(a->K, tile_n);
+  q.n_acc = 512 / tile_n > WS_MAX_ACC ? WS_MAX_ACC : 512 / tile_n;
+  q.acc_shift = ilog2(q.n_acc);
+  q.tmem_cols = (uint32_t)(q.n_acc * tile_n);
+
+  // ---- taps per class; x-parity sub-rows ----
+  struct RawTap { int dy, dx, widx; };
+  RawTap raw[WS_MAX_CLASSES][WS_MAX_TAPS];
+  int bmin[2] = {1 << 30, 1 << 30}, bmax[2] = {-(1 << 30), -(1 << 30)};
+  bool sub_used[2] = {false, false};
+  int max_ntaps = 0, max_q = 0;
+  for (int c = 0; c < q.n_classes; ++c) {
+    WsClass& cl = q.cls[c];
+    cl.py = c / q.ostep; cl.px = c % q.ostep;
+    cl.Pi = (a->P - cl.py + q.ostep - 1) / q.ostep;
+    cl.Qj = (a->Q - cl.px + q.ostep - 1) / q.ostep;
+    if (cl.Pi <= 0 || cl.Qj <= 0) return -1;
+    int n = 0;
+    for (int r = 0; r < a->R; ++r)
+      for (int s = 0; s < a->S; ++s) {
+        int dy, dx;
+        if (gather) {
+          dy = r - a->pad; dx = s - a->pad;
+        } else {
+          const int uy = cl.py + a->pad - r, ux = cl.px + a->pad - s;
+          if (((uy % a->stride) + a->stride) % a->stride != 0 || ((ux % a->stride) + a->stride) % a->stride != 0) continue;
+          dy = uy / a->stride; dx = ux / a->stride;
+        }
+        raw[c][n++] = {dy, dx, r * a->S + s};
+        const int par = ((dx % q.sstep) + q.sstep) % q.sstep, b = floor_div(dx, q.sstep);
+        sub_used[par] = true;
+        bmin[par] = b < bmin[par] ? b : bmin[par];
+        bmax[par] = b > bmax[par] ? b : bmax[par];
+      }
+    if (n == 0) return -1;                    // class without taps (bias-only outputs): other kernels handle it
+    cl.ntaps = n;
+    max_ntaps = n > max_ntaps ? n : max_ntaps;
+    max_q = cl.Qj > max_q ? cl.Qj : max_q;
+    int dymin = 1 << 30, dymax = -(1 << 30);
+    for (int t = 0; t < n; ++t) { dymin = raw[c][t].dy < dymin ? raw[c][t].dy : dymin; dymax = raw[c][t].dy > dymax ? raw[c][t].dy : dymax; }
+    cl.dymax = dymax;
+    if ((dymax - dymin) / q.sstep + 1 > q.n_acc - 1) return -1;     // rows in flight must leave one accumulator to drain
+    cl.ylo = dymin > 0 ? dymin : 0;
+    const int yh = (cl.Pi - 1) * q.sstep + dymax;
+    cl.yhi = yh < a->H - 1 ? yh : a->H - 1;
+    if (cl.ylo > cl.yhi) return -1;
+    for (int i = 0; i < cl.Pi; ++i) {         // every output row needs at least one in-bounds source row
+      bool any = false;
+      for (int t = 0; t < n && !any; ++t) { const int y = i * q.sstep + raw[c][t].dy; any = y >= 0 && y < a->H; }
+      if (!any) return -1;
+    }
+  }
+  int sub_index[2] = {-1, -1};
+  q.nsub = 0;
+  int brange = 0;
+  for (int par = 0; par < q.sstep; ++par)
+    if (sub_used[par]) {
+      sub_index[par] = q.nsub++;
+      brange = bmax[par] - bmin[par] > brange ? bmax[par] - bmin[par] : brange;
+    }
+  // ---- column shape: XG output x positions times NG images ----
+  double best = 1e30;
+  for (int xg = 1; xg <= 16; xg *= 2) {
+    const double eff = (double)max_q / (icf::cdiv(max_q, xg) * xg);
+    const double cost = (1.0 / eff) * (1.0 + 0.25 * brange / xg);
+    if (cost < best - 1e-9 || (cost < best + 1e-9 && xg > q.XG)) { best = cost; q.XG = xg; }
+  }
+  q.NG = 128 / q.XG;
+  q.ng_shift = ilog2(q.NG);
+  const int hx = q.XG + brange;
+  if (hx * q.sstep > 256) return -1;
+  q.kc_bytes = (uint32_t)(hx * q.NG) * 128u;
+  q.sub_bytes = q.kc_bytes * (uint32_t)q.kchunks;
+  q.slot_bytes = q.sub_bytes * (uint32_t)q.nsub;
+  q.slab_bytes = (uint32_t)(max_ntaps * q.kchunks * tile_n) * 128u;
+  if ((int64_t)q.slab_bytes + 2 * (int64_t)q.slot_bytes > WS_SMEM_BUDGET) return -1;
+  q.n_slots = (int)((WS_SMEM_BUDGET - (int64_t)q.slab_bytes) / q.slot_bytes);
+  if (q.n_slots > WS_MAX_SLOTS) q.n_slots = WS_MAX_SLOTS;
+  q.tiles_n = icf::cdiv(a->N, q.NG);
+
+  // ---- tap tables, CTA partition over (class, k-tile) ----
+  double work[WS_MAX_CLASSES], total = 0.0;
+  for (int c = 0; c < q.n_classes; ++c) {
+    WsClass& cl = q.cls[c];
+    cl.tiles_x = icf::cdiv(cl.Qj, q.XG);
+    for (int t = 0; t < cl.ntaps; ++t) {
+      const int dx = raw[c][t].dx;
+      const int par = ((dx % q.sstep) + q.sstep) % q.sstep, b = floor_div(dx, q.sstep);
+      cl.taps[t].dy = (int16_t)raw[c][t].dy;
+      cl.taps[t].widx = (int16_t)raw[c][t].widx;
+      cl.taps[t].a_off = (uint32_t)sub_index[par] * q.sub_bytes + (uint32_t)((b - bmin[par]) * q.NG) * 128u;
+    }
+    for (int par = 0; par < q.sstep; ++par)
+      if (sub_used[par]) cl.x0[sub_index[par]] = bmin[par] * q.sstep + par;
+    work[c] = (double)cl.tiles_x * cl.Pi * cl.ntaps;
+    total += work[c];
+  }
+  const int budget = sm_count();
+  int grid = 0;
+  for (int c = 0; c < q.n_classes; ++c) {
+    WsClass& cl = q.cls[c];
+    const int ncols = q.tiles_n * cl.tiles_x;
+    int per_k = (int)((double)budget * work[c] / total / q.tiles_k);
+    if (per_k < 1) per_k = 1;
+    if (per_k > ncols) per_k = ncols;
+    cl.cta_begin = grid;
+    cl.cta_count = per_k * q.tiles_k;
+    grid += cl.cta_count;
+  }
+  q.act = a->act; q.slope = a->slope; q.out_f32 = a->out_f32; q.mask_pitch = a->mask_pitch;
+  q.bias = a->bias; q.mask = a->out_mask; q.dst = a->dst;
+
+  CUtensorMap ma, mb;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)a->C, (cuuint64_t)a->N, (cuuint64_t)a->W, (cuuint64_t)a->H};
+    cuuint64_t str[3] = {(cuuint64_t)a->H * a->W * a->in_pitch * 2, (cuuint64_t)a->in_pitch * 2,
+                         (cuuint64_t)a->W * a->in_pitch * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)q.NG, (cuuint32_t)(hx * q.sstep), 1};
+    cuuint32_t est[4] = {1, 1, (cuuint32_t)q.sstep, 1};
+    if (int r = encode_map(&ma, a->src, 4, dims, str, box, est)) return r;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)taps_all * a->w_pitch, (cuuint64_t)a->w_rows};
+    cuuint64_t str[1] = {(cuuint64_t)taps_all * a->w_pitch * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)tile_n};
+    cuuint32_t est[2] = {1, 1};
+    if (int r = encode_map(&mb, a->w, 2, dims, str, box, est)) return r;
+  }
+  // shared memory: always more than half an SM's worth so that exactly one CTA (and one TMEM allocation) is resident
+  size_t smem = (size_t)q.slab_bytes + (size_t)q.n_slots * q.slot_bytes + 1024 + 1024;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  int r;
+  switch (tile_n) {
+    case 16: r = launch_ws<16>(ma, mb, q, grid, smem, st); break;
+    case 32: r = launch_ws<32>(ma, mb, q, grid, smem, st); break;
+    default: r = launch_ws<64>(ma, mb, q, grid, smem, st); break;
+  }
+  if (r) return r;
+  if (a->stats) {
+    if (a->out_f32) { icf::set_error("row-streaming conv: BatchNorm statistics need a bf16 destination"); return 1; }
+    return icf_launch_col_stats(a->dst, ICF_BF16, a->out_pitch, (int64_t)a->N * a->P * a->Q, a->K, a->stats, st);
+  }
+  return 0;
+}

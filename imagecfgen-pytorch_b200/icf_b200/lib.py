@@ -82,6 +82,7 @@ _SIGS = {
     "icf_version": (_i32, []),
     "icf_tc_enabled": (_i32, []),
     "icf_set_tc_enabled": (None, [_i32]),
+    "icf_last_conv_path": (_i32, []),
     "icf_conv_forward": (_i32, [C.POINTER(ConvArgs), _vp]),
     "icf_conv_wgrad": (_i32, [C.POINTER(WgradArgs), _vp]),
     "icf_pack": (_i32, [_vp, _vp, _i32, C.POINTER(Perm), _vp]),

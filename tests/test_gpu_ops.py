@@ -42,6 +42,9 @@ CONV_CASES = [  # N, C, H, K, k, stride, pad
     (3, 5, 28, 64, 3, 2, 1), (2, 64, 14, 128, 4, 2, 1), (2, 128, 7, 256, 4, 2, 1), (5, 256, 3, 512, 4, 2, 1),
     (7, 512, 1, 512, 1, 2, 0), (2, 5, 28, 32, 5, 1, 0), (2, 32, 24, 64, 4, 2, 0), (3, 7, 32, 64, 5, 2, 1),
     (130, 64, 3, 1, 1, 1, 0), (2, 1024, 1, 1024, 1, 1, 0),
+    # several image blocks / columns per persistent CTA of the row-streaming kernel
+    (300, 5, 28, 32, 5, 1, 0), (200, 32, 24, 64, 4, 2, 0), (150, 64, 11, 128, 4, 1, 0), (260, 64, 14, 40, 4, 2, 1),
+    (140, 24, 12, 16, 3, 1, 1),
 ]
 
 
@@ -74,6 +77,7 @@ def test_conv_gather(case, code):
 CONVT_CASES = [  # N, C, H, K, k, stride, pad, opad
     (3, 771, 1, 512, 3, 1, 0, 0), (2, 512, 3, 256, 3, 2, 0, 0), (2, 256, 7, 128, 3, 2, 1, 0),
     (2, 128, 13, 64, 3, 2, 1, 0), (3, 64, 25, 1, 4, 1, 0, 0), (2, 64, 4, 32, 5, 2, 2, 1), (2, 64, 16, 1, 5, 2, 2, 1),
+    (260, 64, 25, 1, 4, 1, 0, 0), (200, 32, 24, 5, 5, 1, 0, 0), (150, 128, 13, 64, 3, 2, 1, 0), (130, 64, 11, 32, 4, 2, 0, 0),
 ]
 
 
