@@ -29,11 +29,17 @@ using namespace icf_tc;
 constexpr int WS_THREADS = 192;
 constexpr int WS_MAX_CLASSES = 4, WS_MAX_TAPS = 25, WS_MAX_SUBS = 2, WS_MAX_ACC = 16, WS_MAX_SLOTS = 8;
 constexpr int WS_SMEM_BUDGET = 220 * 1024;
+constexpr int WS_MAX_GROUPS = 8;
 
 struct WsTap {
   int16_t dy;        // source row = i*sstep + dy
   int16_t widx;      // tap index r*S+s into the packed weights
-  uint32_t a_off;    // byte offset of this tap's operand inside a slot (sub-row + x shift)
+  uint32_t a_off16;  // offset (16-byte units) of this tap's operand inside a slot (sub-row + x shift)
+};
+
+struct WsGroup {     // taps that share dy (one filter row): they feed the same output row from one source row
+  int16_t dy;
+  int8_t first, count;
 };
 
 struct WsClass {
@@ -41,6 +47,8 @@ struct WsClass {
   int ntaps, ylo, yhi, dymax;
   int x0[WS_MAX_SUBS];         // TMA x start = j0*sstep + x0[sub]
   int tiles_x, cta_begin, cta_count;
+  int ngroups;
+  WsGroup grp[WS_MAX_GROUPS];
   WsTap taps[WS_MAX_TAPS];
 };
 
@@ -61,7 +69,8 @@ struct WsParams {
   WsClass cls[WS_MAX_CLASSES];
 };
 
-template <int TILE_N>
+// KD > 0: single 64-channel K chunk of KD 16-wide MMA steps (fully unrolled issue loop); KD == 0: generic
+template <int TILE_N, int KD>
 __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_constant__ CUtensorMap map_a,
                                                              const __grid_constant__ CUtensorMap map_b,
                                                              const __grid_constant__ WsParams p) {
@@ -138,54 +147,71 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, TILE_N, 0, 0);
-      mbar_wait(w_full, 0);
-      tc_fence_after();
-      int s = 0;
-      uint32_t ph = 0;
-      int g_base = 0;                       // sequence number of this column's output row 0
-      for (int col = r0; col < ncols; col += rstep) {
-        uint32_t started = 0;               // bit per accumulator: output row has received its first MMA
-        int next_done = 0;
-        for (int y = cl.ylo; y <= cl.yhi; ++y) {
-          mbar_wait(slot_full(s), ph);
-          tc_fence_after();
-          const uint32_t base = slots_addr + (uint32_t)s * p.slot_bytes;
-          for (int t = 0; t < cl.ntaps; ++t) {
-            const int num = y - cl.taps[t].dy;
-            if (num < 0) continue;
-            const int i = p.sstep == 1 ? num : (num >> 1);
-            if (i * p.sstep != num || i >= cl.Pi) continue;
-            const int g = g_base + i, acc = g & (p.n_acc - 1);
-            const uint32_t bit = 1u << acc;
-            if (!(started & bit)) {
-              mbar_wait(acc_empty(acc), ((uint32_t)(g >> p.acc_shift) & 1u) ^ 1u);
-              tc_fence_after();
-            }
-            const uint32_t d_tmem = tmem_base + (uint32_t)acc * TILE_N;
-            const uint32_t a_addr = base + cl.taps[t].a_off, b_addr = slab_addr + (uint32_t)(t * p.kchunks) * W_BLOCK;
-            for (int kc = 0; kc < p.kchunks; ++kc) {
-              const int nk = (kc == p.kchunks - 1) ? p.kdepth_last : 4;
-              const uint64_t adesc = make_desc(a_addr + kc * p.kc_bytes, 16, 1024);
-              const uint64_t bdesc = make_desc(b_addr + kc * W_BLOCK, 16, 1024);
-              for (int k = 0; k < nk; ++k)
-                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((started & bit) || kc || k) ? 1u : 0u);
-            }
-            started |= bit;
+    // ===== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues =====
+    constexpr uint32_t idesc = make_idesc(128, TILE_N, 0, 0);
+    constexpr uint32_t WB16 = W_BLOCK >> 4;
+    const uint32_t leader = elect_one();
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    const uint64_t d0 = make_desc(0, 16, 1024);
+    const uint32_t desc_hi = (uint32_t)(d0 >> 32), lbo_lo = (uint32_t)d0;     // low word without an address
+    const uint32_t b_lo0 = ((slab_addr >> 4) & 0x3FFFu) | lbo_lo;
+    const uint32_t kc16 = p.kc_bytes >> 4;
+    int s = 0;
+    uint32_t ph = 0;
+    int g_base = 0;                       // sequence number of this column's output row 0
+    for (int col = r0; col < ncols; col += rstep) {
+      uint32_t started = 0;               // bit per accumulator: output row has received its first MMA
+      int next_done = 0;
+      for (int y = cl.ylo; y <= cl.yhi; ++y) {
+        mbar_wait(slot_full(s), ph);
+        tc_fence_after();
+        const uint32_t a_lo0 = (((slots_addr + (uint32_t)s * p.slot_bytes) >> 4) & 0x3FFFu) | lbo_lo;
+        for (int gi = 0; gi < cl.ngroups; ++gi) {
+          const int num = y - cl.grp[gi].dy;
+          if (num < 0) continue;
+          const int i = p.sstep == 1 ? num : (num >> 1);
+          if (i * p.sstep != num || i >= cl.Pi) continue;
+          const int g = g_base + i, acc = g & (p.n_acc - 1);
+          const uint32_t bit = 1u << acc;
+          if (!(started & bit)) {
+            mbar_wait(acc_empty(acc), ((uint32_t)(g >> p.acc_shift) & 1u) ^ 1u);
+            tc_fence_after();
           }
-          umma_commit(slot_empty(s));
-          if (++s == p.n_slots) { s = 0; ph ^= 1; }
-          while (next_done < cl.Pi && (next_done * p.sstep + cl.dymax <= y || y == cl.yhi)) {
-            const int acc = (g_base + next_done) & (p.n_acc - 1);
-            umma_commit(acc_full(acc));     // host guarantees every output row has an in-bounds source row
-            started &= ~(1u << acc);
-            ++next_done;
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * TILE_N;
+          uint32_t accum = (started & bit) ? 1u : 0u;
+          const int t0 = cl.grp[gi].first, t1 = t0 + cl.grp[gi].count;
+          for (int t = t0; t < t1; ++t) {
+            const uint32_t a_lo = a_lo0 + cl.taps[t].a_off16;
+            const uint32_t b_lo = b_lo0 + (uint32_t)(t * p.kchunks) * WB16;
+            if (KD > 0) {
+#pragma unroll
+              for (int k = 0; k < KD; ++k) {
+                umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, accum, leader);
+                accum = 1u;
+              }
+            } else {
+              for (int kc = 0; kc < p.kchunks; ++kc) {
+                const int nk = (kc == p.kchunks - 1) ? p.kdepth_last : 4;
+                for (int k = 0; k < nk; ++k) {
+                  umma_bf16_lo(d_tmem, a_lo + kc * kc16 + 2 * k, b_lo + kc * WB16 + 2 * k, desc_hi, idesc, accum, leader);
+                  accum = 1u;
+                }
+              }
+            }
           }
+          started |= bit;
         }
-        g_base += cl.Pi;
+        umma_commit_if(slot_empty(s), leader);
+        if (++s == p.n_slots) { s = 0; ph ^= 1; }
+        while (next_done < cl.Pi && (next_done * p.sstep + cl.dymax <= y || y == cl.yhi)) {
+          const int acc = (g_base + next_done) & (p.n_acc - 1);
+          umma_commit_if(acc_full(acc), leader);   // host guarantees every output row has an in-bounds source row
+          started &= ~(1u << acc);
+          ++next_done;
+        }
       }
+      g_base += cl.Pi;
     }
   } else {
     // ===== epilogue: TMEM lane m = x_local*NG + n_local =====
@@ -261,16 +287,16 @@ int sm_count() {
   return n;
 }
 
-template <int TILE_N>
+template <int TILE_N, int KD>
 int launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, const WsParams& p, int grid, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_ws_kernel<TILE_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_ws_kernel<TILE_N, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     ICF_REQUIRE(e == cudaSuccess, "row-streaming conv: cannot reserve %zu B of shared memory: %s", smem,
                 cudaGetErrorString(e));
     configured = smem;
   }
-  conv_ws_kernel<TILE_N><<<(unsigned)grid, WS_THREADS, smem, st>>>(ma, mb, p);
+  conv_ws_kernel<TILE_N, KD><<<(unsigned)grid, WS_THREADS, smem, st>>>(ma, mb, p);
   return icf::check_launch("conv_ws");
 }
 
@@ -386,7 +412,15 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
       const int par = ((dx % q.sstep) + q.sstep) % q.sstep, b = floor_div(dx, q.sstep);
       cl.taps[t].dy = (int16_t)raw[c][t].dy;
       cl.taps[t].widx = (int16_t)raw[c][t].widx;
-      cl.taps[t].a_off = (uint32_t)sub_index[par] * q.sub_bytes + (uint32_t)((b - bmin[par]) * q.NG) * 128u;
+      cl.taps[t].a_off16 = ((uint32_t)sub_index[par] * q.sub_bytes + (uint32_t)((b - bmin[par]) * q.NG) * 128u) >> 4;
+      if (t == 0 || raw[c][t].dy != raw[c][t - 1].dy) {
+        if (cl.ngroups == WS_MAX_GROUPS) return -1;
+        cl.grp[cl.ngroups].dy = (int16_t)raw[c][t].dy;
+        cl.grp[cl.ngroups].first = (int8_t)t;
+        cl.grp[cl.ngroups].count = 0;
+        ++cl.ngroups;
+      }
+      ++cl.grp[cl.ngroups - 1].count;
     }
     for (int par = 0; par < q.sstep; ++par)
       if (sub_used[par]) cl.x0[sub_index[par]] = bmin[par] * q.sstep + par;
@@ -428,11 +462,21 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   size_t smem = (size_t)q.slab_bytes + (size_t)q.n_slots * q.slot_bytes + 1024 + 1024;
   if (smem < 120 * 1024) smem = 120 * 1024;
   int r;
-  switch (tile_n) {
-    case 16: r = launch_ws<16>(ma, mb, q, grid, smem, st); break;
-    case 32: r = launch_ws<32>(ma, mb, q, grid, smem, st); break;
-    default: r = launch_ws<64>(ma, mb, q, grid, smem, st); break;
+  const int kd = q.kchunks == 1 ? q.kdepth_last : 0;
+#define ICF_WS_CASE(TN)                                                        \
+  switch (kd) {                                                                \
+    case 1: r = launch_ws<TN, 1>(ma, mb, q, grid, smem, st); break;            \
+    case 2: r = launch_ws<TN, 2>(ma, mb, q, grid, smem, st); break;            \
+    case 3: r = launch_ws<TN, 3>(ma, mb, q, grid, smem, st); break;            \
+    case 4: r = launch_ws<TN, 4>(ma, mb, q, grid, smem, st); break;            \
+    default: r = launch_ws<TN, 0>(ma, mb, q, grid, smem, st); break;           \
   }
+  switch (tile_n) {
+    case 16: ICF_WS_CASE(16) break;
+    case 32: ICF_WS_CASE(32) break;
+    default: ICF_WS_CASE(64) break;
+  }
+#undef ICF_WS_CASE
   if (r) return r;
   if (a->stats) {
     if (a->out_f32) { icf::set_error("row-streaming conv: BatchNorm statistics need a bf16 destination"); return 1; }
