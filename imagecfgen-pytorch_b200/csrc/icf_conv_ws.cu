@@ -17,16 +17,20 @@
 //   * Stride-2 gathers read each source row as two x-parity sub-rows (TMA element stride 2); transposed forms are
 //     unit-stride gathers per output-parity class (no zero insertion).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// Warp roles: warp 0 = TMA producer, warps 1..WS_ISSUERS = MMA issuers (small-N MMAs are issue-bound, so the
+// output rows are dealt round-robin to several issuing warps; warp 1 also owns the TMEM allocation), last four
+// warps = epilogue.
 #include "icf_epilogue.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace {
 
 using namespace icf_tc;
 
-constexpr int WS_THREADS = 192;
+constexpr int WS_ISSUERS = 4;                       // MMA-issuing warps: output row i belongs to issuer i % WS_ISSUERS
+constexpr int WS_THREADS = 32 * (1 + WS_ISSUERS + 4);
 constexpr int WS_MAX_CLASSES = 4, WS_MAX_TAPS = 25, WS_MAX_SUBS = 2, WS_MAX_ACC = 16, WS_MAX_SLOTS = 8;
 constexpr int WS_SMEM_BUDGET = 220 * 1024;
 constexpr int WS_MAX_GROUPS = 8;
@@ -39,6 +43,8 @@ struct WsTap {
 
 struct WsGroup {     // taps that share dy (one filter row): they feed the same output row from one source row
   int16_t dy;
+  int16_t dprev;     // dy minus the next smaller dy that feeds the same output rows (32767: none) — the group opens
+                     // its output row (accumulate = 0) iff the previous contributor's source row lies above ylo
   int8_t first, count;
 };
 
@@ -66,10 +72,22 @@ struct WsParams {
   const float* bias;
   const float* mask;
   void* dst;
+  unsigned long long* dbg;     // optional per-role cycle counters of CTA 0 (env ICF_WS_DEBUG), else NULL
   WsClass cls[WS_MAX_CLASSES];
 };
 
 // KD > 0: single 64-channel K chunk of KD 16-wide MMA steps (fully unrolled issue loop); KD == 0: generic
+#define WS_TIMED_WAIT(counter, bar, par)                    \
+  do {                                                     \
+    if (dbg_on) {                                          \
+      const long long t_ = clock64();                      \
+      mbar_wait(bar, par);                                 \
+      counter += clock64() - t_;                           \
+    } else {                                               \
+      mbar_wait(bar, par);                                 \
+    }                                                      \
+  } while (0)
+
 template <int TILE_N, int KD>
 __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_constant__ CUtensorMap map_a,
                                                              const __grid_constant__ CUtensorMap map_b,
@@ -104,7 +122,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     prefetch_tmap(&map_b);
     for (int s = 0; s < WS_MAX_SLOTS; ++s) {
       mbar_init(slot_full(s), 1);
-      mbar_init(slot_empty(s), 1);
+      mbar_init(slot_empty(s), WS_ISSUERS);
     }
     for (int a = 0; a < WS_MAX_ACC; ++a) {
       mbar_init(acc_full(a), 1);
@@ -119,6 +137,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t slab_addr = smem_u32(wslab), slots_addr = smem_u32(slots);
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
+  long long w0 = 0, w1 = 0;                 // cycles spent in this role's two kinds of barrier waits
+  const long long t_begin = dbg_on ? clock64() : 0;
   constexpr uint32_t W_BLOCK = TILE_N * 128;      // one (tap, K chunk) block of the weight slab
 
   if (warp == 0) {
@@ -135,7 +156,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         const int jt = col % cl.tiles_x, nt = col / cl.tiles_x;
         const int n0 = nt * p.NG, xs = jt * p.XG * p.sstep;
         for (int y = cl.ylo; y <= cl.yhi; ++y) {
-          mbar_wait(slot_empty(s), ph ^ 1);
+          WS_TIMED_WAIT(w0, slot_empty(s), ph ^ 1);
           mbar_expect_tx(slot_full(s), p.slot_bytes);
           const uint32_t base = slots_addr + (uint32_t)s * p.slot_bytes;
           for (int sub = 0; sub < p.nsub; ++sub)
@@ -145,11 +166,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
           if (++s == p.n_slots) { s = 0; ph ^= 1; }
         }
       }
+      if (dbg_on) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = w0; }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues =====
+  } else if (warp <= WS_ISSUERS) {
+    // ===== MMA issuers: whole warp runs the control flow, one elected lane issues.  Issuer wi owns the output rows
+    // i with i % WS_ISSUERS == wi, so all MMAs into one accumulator come from one thread (ordered). =====
     constexpr uint32_t idesc = make_idesc(128, TILE_N, 0, 0);
     constexpr uint32_t WB16 = W_BLOCK >> 4;
+    const int wi = warp - 1;
     const uint32_t leader = elect_one();
     mbar_wait(w_full, 0);
     tc_fence_after();
@@ -157,29 +181,30 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     const uint32_t desc_hi = (uint32_t)(d0 >> 32), lbo_lo = (uint32_t)d0;     // low word without an address
     const uint32_t b_lo0 = ((slab_addr >> 4) & 0x3FFFu) | lbo_lo;
     const uint32_t kc16 = p.kc_bytes >> 4;
+    const int Pi = cl.Pi, ylo = cl.ylo, yhi = cl.yhi, dymax = cl.dymax, ngroups = cl.ngroups;
+    const int amask = p.n_acc - 1;
     int s = 0;
     uint32_t ph = 0;
     int g_base = 0;                       // sequence number of this column's output row 0
     for (int col = r0; col < ncols; col += rstep) {
-      uint32_t started = 0;               // bit per accumulator: output row has received its first MMA
       int next_done = 0;
-      for (int y = cl.ylo; y <= cl.yhi; ++y) {
-        mbar_wait(slot_full(s), ph);
+      for (int y = ylo; y <= yhi; ++y) {
+        WS_TIMED_WAIT(w0, slot_full(s), ph);
         tc_fence_after();
         const uint32_t a_lo0 = (((slots_addr + (uint32_t)s * p.slot_bytes) >> 4) & 0x3FFFu) | lbo_lo;
-        for (int gi = 0; gi < cl.ngroups; ++gi) {
-          const int num = y - cl.grp[gi].dy;
-          if (num < 0) continue;
+        for (int gi = 0; gi < ngroups; ++gi) {
+          const int dy = cl.grp[gi].dy;
+          const int num = y - dy;
           const int i = p.sstep == 1 ? num : (num >> 1);
-          if (i * p.sstep != num || i >= cl.Pi) continue;
-          const int g = g_base + i, acc = g & (p.n_acc - 1);
-          const uint32_t bit = 1u << acc;
-          if (!(started & bit)) {
-            mbar_wait(acc_empty(acc), ((uint32_t)(g >> p.acc_shift) & 1u) ^ 1u);
+          if (num < 0 || i >= Pi || (i & (WS_ISSUERS - 1)) != wi || (p.sstep == 2 && (num & 1))) continue;
+          const int g = g_base + i, acc = g & amask;
+          uint32_t accum = 1u;
+          if (y - cl.grp[gi].dprev < ylo) {          // first in-bounds contributor of output row i
+            WS_TIMED_WAIT(w1, acc_empty(acc), ((uint32_t)(g >> p.acc_shift) & 1u) ^ 1u);
             tc_fence_after();
+            accum = 0u;
           }
           const uint32_t d_tmem = tmem_base + (uint32_t)acc * TILE_N;
-          uint32_t accum = (started & bit) ? 1u : 0u;
           const int t0 = cl.grp[gi].first, t1 = t0 + cl.grp[gi].count;
           for (int t = t0; t < t1; ++t) {
             const uint32_t a_lo = a_lo0 + cl.taps[t].a_off16;
@@ -200,19 +225,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
               }
             }
           }
-          started |= bit;
         }
-        umma_commit_if(slot_empty(s), leader);
+        umma_commit_if(slot_empty(s), leader);       // arrives once this issuer's MMAs on the slot have retired
         if (++s == p.n_slots) { s = 0; ph ^= 1; }
-        while (next_done < cl.Pi && (next_done * p.sstep + cl.dymax <= y || y == cl.yhi)) {
-          const int acc = (g_base + next_done) & (p.n_acc - 1);
-          umma_commit_if(acc_full(acc), leader);   // host guarantees every output row has an in-bounds source row
-          started &= ~(1u << acc);
+        while (next_done < Pi && (next_done * p.sstep + dymax <= y || y == yhi)) {
+          if ((next_done & (WS_ISSUERS - 1)) == wi)
+            umma_commit_if(acc_full((g_base + next_done) & amask), leader);   // every row has an in-bounds source row
           ++next_done;
         }
       }
-      g_base += cl.Pi;
+      g_base += Pi;
     }
+    if (dbg_on && lane == 0 && wi == 0) { p.dbg[2] = clock64() - t_begin; p.dbg[3] = w0; p.dbg[4] = w1; }
   } else {
     // ===== epilogue: TMEM lane m = x_local*NG + n_local =====
     const int q4 = warp & 3;
@@ -220,7 +244,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     const int x_local = m >> p.ng_shift, n_local = m & (p.NG - 1);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
     // bias tile -> shared memory (zero where absent / beyond K), visible to the four epilogue warps
-    for (int j = (int)threadIdx.x - 64; j < TILE_N; j += 128) sbias[j] = (p.bias && k0 + j < p.K) ? __ldg(p.bias + k0 + j) : 0.f;
+    for (int j = (int)threadIdx.x - 32 * (1 + WS_ISSUERS); j < TILE_N; j += 128) sbias[j] = (p.bias && k0 + j < p.K) ? __ldg(p.bias + k0 + j) : 0.f;
     asm volatile("bar.sync 1, 128;" ::: "memory");
     const int esize = p.out_f32 ? 4 : 2;
     int g = 0;
@@ -243,14 +267,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
       const int64_t row_step = (int64_t)p.ostep * p.Q * p.out_pitch * esize;
       for (int i = 0; i < cl.Pi; ++i, ++g, orow += row_step) {
         const int acc = g & (p.n_acc - 1);
-        mbar_wait(acc_full(acc), (uint32_t)(g >> p.acc_shift) & 1u);
+        WS_TIMED_WAIT(w0, acc_full(acc), (uint32_t)(g >> p.acc_shift) & 1u);
         tc_fence_after();
+        const long long t_ld = dbg_on ? clock64() : 0;
 #pragma unroll
         for (int c0 = 0; c0 < TILE_N; c0 += 32) {
           uint32_t va[16], vb[16];
           tmem_ld16(lane_addr + (uint32_t)(acc * TILE_N + c0), va);
           if (TILE_N > 16) tmem_ld16(lane_addr + (uint32_t)(acc * TILE_N + c0 + 16), vb);
           tmem_ld_wait();
+          if (dbg_on && c0 + 32 >= TILE_N) w1 += clock64() - t_ld;
           if (c0 + 32 >= TILE_N) {          // accumulator fully read: hand it back before the math and stores
             tc_fence_before();
             __syncwarp();
@@ -268,6 +294,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         }
       }
     }
+    if (dbg_on && threadIdx.x == 32 * (1 + WS_ISSUERS)) { p.dbg[5] = clock64() - t_begin; p.dbg[6] = w0; p.dbg[7] = w1; }
   }
   tc_fence_before();
   __syncthreads();
@@ -422,6 +449,14 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
       }
       ++cl.grp[cl.ngroups - 1].count;
     }
+    for (int g1 = 0; g1 < cl.ngroups; ++g1) {        // previous contributor to the same output row: next smaller dy
+      int best = -(1 << 30);
+      for (int g2 = 0; g2 < cl.ngroups; ++g2) {
+        const int d2 = cl.grp[g2].dy, d1 = cl.grp[g1].dy;
+        if (d2 < d1 && d2 > best) best = d2;
+      }
+      cl.grp[g1].dprev = best == -(1 << 30) ? (int16_t)32767 : (int16_t)(cl.grp[g1].dy - best);
+    }
     for (int par = 0; par < q.sstep; ++par)
       if (sub_used[par]) cl.x0[sub_index[par]] = bmin[par] * q.sstep + par;
     work[c] = (double)cl.tiles_x * cl.Pi * cl.ntaps;
@@ -441,6 +476,13 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   }
   q.act = a->act; q.slope = a->slope; q.out_f32 = a->out_f32; q.mask_pitch = a->mask_pitch;
   q.bias = a->bias; q.mask = a->out_mask; q.dst = a->dst;
+  static unsigned long long* dbg_buf = []() -> unsigned long long* {
+    const char* e = getenv("ICF_WS_DEBUG");
+    void* d = nullptr;
+    if (e && e[0] && e[0] != '0' && cudaMalloc(&d, 64) == cudaSuccess) cudaMemset(d, 0, 64);
+    return reinterpret_cast<unsigned long long*>(d);
+  }();
+  q.dbg = dbg_buf;
 
   CUtensorMap ma, mb;
   {
@@ -478,6 +520,16 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   }
 #undef ICF_WS_CASE
   if (r) return r;
+  if (q.dbg) {
+    unsigned long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, q.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr,
+            "[icf ws] K=%d C=%d R=%d stride=%d form=%d tile_n=%d XG=%d NG=%d slots=%d slot=%uB slab=%uB grid=%d | CTA0 cycles: "
+            "producer %llu (wait empty %llu) | mma %llu (wait full %llu, wait acc %llu) | epilogue %llu (wait acc_full %llu, tmem ld %llu)\n",
+            a->K, a->C, a->R, a->stride, a->form, tile_n, q.XG, q.NG, q.n_slots, q.slot_bytes, q.slab_bytes, grid, h[0], h[1],
+            h[2], h[3], h[4], h[5], h[6], h[7]);
+  }
   if (a->stats) {
     if (a->out_f32) { icf::set_error("row-streaming conv: BatchNorm statistics need a bf16 destination"); return 1; }
     return icf_launch_col_stats(a->dst, ICF_BF16, a->out_pitch, (int64_t)a->N * a->P * a->Q, a->K, a->stats, st);
