@@ -186,7 +186,10 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
 #pragma unroll
         for (int j = 0; j < 16; ++j) mk[j] = 1.f;
       }
-      epi16(v, sbias + c0, mk, p.act, p.slope, nv < 16 ? nv : 16, p.out_f32, orow + c0 * esize);
+      const int nvl = nv < 16 ? nv : 16;
+      int npad = (nvl + 7) & ~7;
+      if (k0 + c0 + npad > p.out_pitch) npad = nvl;
+      epi16(v, sbias + c0, mk, p.act, p.slope, nvl, npad, p.out_f32, orow + c0 * esize);
     }
   }
   tc_fence_before();

@@ -72,6 +72,7 @@ struct WsParams {
   const float* bias;
   const float* mask;
   void* dst;
+  int tma_store;               // 1: epilogue stages bf16 rows in shared memory and leaves through a TMA tensor store
   unsigned long long* dbg;     // optional per-role cycle counters of CTA 0 (env ICF_WS_DEBUG), else NULL
   WsClass cls[WS_MAX_CLASSES];
 };
@@ -90,13 +91,15 @@ struct WsParams {
 
 template <int TILE_N, int KD>
 __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                             const __grid_constant__ CUtensorMap map_b,
-                                                             const __grid_constant__ WsParams p) {
+                                                                const __grid_constant__ CUtensorMap map_b,
+                                                                const __grid_constant__ CUtensorMap map_o,
+                                                                const __grid_constant__ WsParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wslab = smem;
   uint8_t* slots = smem + p.slab_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(slots + (size_t)p.n_slots * p.slot_bytes);
+  uint8_t* stage = slots + (size_t)p.n_slots * p.slot_bytes;      // 2 x [128 rows][TILE_N] bf16 (TMA-store epilogue)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 2 * 128 * TILE_N * 2);
   // barrier layout: slot_full[8] slot_empty[8] acc_full[16] acc_empty[16] w_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WS_MAX_SLOTS + 2 * WS_MAX_ACC + 1);
   float* sbias = reinterpret_cast<float*>(bars + 64);          // TILE_N floats, 512 B past the barriers
@@ -120,6 +123,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_b);
+    if (p.tma_store) prefetch_tmap(&map_o);
     for (int s = 0; s < WS_MAX_SLOTS; ++s) {
       mbar_init(slot_full(s), 1);
       mbar_init(slot_empty(s), WS_ISSUERS);
@@ -261,6 +265,53 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < TILE_N; ++j) mk[j] = 1.f;
       }
+      if (p.tma_store) {
+        // ---- staged epilogue: registers -> swizzled shared-memory rows -> one TMA tensor store per output row ----
+        constexpr uint32_t ROW_B = TILE_N * 2, BUF_B = 128 * ROW_B;
+        const uint32_t sw = TILE_N == 64 ? (uint32_t)(m & 7) : (TILE_N == 32 ? (uint32_t)((m >> 1) & 3) : (uint32_t)((m >> 2) & 1));
+        const uint32_t srow = smem_u32(stage) + (uint32_t)m * ROW_B;
+        const bool issuer = (int)threadIdx.x == 32 * (1 + WS_ISSUERS);
+        const int ox = cl.px + jt * p.XG * p.ostep, n0 = nt * p.NG;
+        for (int i = 0; i < cl.Pi; ++i, ++g) {
+          const int acc = g & (p.n_acc - 1);
+          WS_TIMED_WAIT(w0, acc_full(acc), (uint32_t)(g >> p.acc_shift) & 1u);
+          tc_fence_after();
+          const long long t_ld = dbg_on ? clock64() : 0;
+          uint4 outv[TILE_N / 8];
+#pragma unroll
+          for (int c0 = 0; c0 < TILE_N; c0 += 32) {
+            uint32_t va[16], vb[16];
+            tmem_ld16(lane_addr + (uint32_t)(acc * TILE_N + c0), va);
+            if (TILE_N > 16) tmem_ld16(lane_addr + (uint32_t)(acc * TILE_N + c0 + 16), vb);
+            tmem_ld_wait();
+            if (dbg_on && c0 + 32 >= TILE_N) w1 += clock64() - t_ld;
+            if (c0 + 32 >= TILE_N) {        // accumulator fully read: hand it back before the math
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(acc_empty(acc));
+            }
+            const int nv = p.K - (k0 + c0);
+            epi16_pack(va, sbias + c0, *reinterpret_cast<const float(*)[16]>(&mk[c0]), p.act, p.slope,
+                       nv < 0 ? 0 : (nv < 16 ? nv : 16), outv[c0 / 8], outv[c0 / 8 + 1]);
+            if (TILE_N > 16)
+              epi16_pack(vb, sbias + c0 + 16, *reinterpret_cast<const float(*)[16]>(&mk[TILE_N > 16 ? c0 + 16 : 0]), p.act,
+                         p.slope, nv < 16 ? 0 : (nv < 32 ? nv - 16 : 16), outv[TILE_N > 16 ? c0 / 8 + 2 : 0],
+                         outv[TILE_N > 16 ? c0 / 8 + 3 : 1]);
+          }
+          const uint32_t buf = (uint32_t)(g & 1) * BUF_B;
+          if (issuer) bulk_wait_read<1>();          // the store that last read this buffer has drained it
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < TILE_N / 8; ++c) sts128(srow + buf + (((uint32_t)c ^ sw) << 4), outv[c]);
+          fence_proxy_async();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (issuer) {
+            tma_store_4d(&map_o, smem_u32(stage) + buf, k0, n0, ox, cl.py + i * p.ostep);
+            bulk_commit();
+          }
+        }
+        continue;
+      }
       // destination of output row 0 of this thread's pixel column, channel k0
       uint8_t* orow = reinterpret_cast<uint8_t*>(p.dst) +
                       ((((int64_t)(valid ? n : 0) * p.P + cl.py) * p.Q + cl.px + (int64_t)(valid ? jj : 0) * p.ostep) * p.out_pitch + k0) * esize;
@@ -284,16 +335,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
           }
           if (valid) {
             const int nv = p.K - (k0 + c0);
-            if (nv > 0)
-              epi16(va, sbias + c0, *reinterpret_cast<const float(*)[16]>(&mk[c0]), p.act, p.slope, nv < 16 ? nv : 16,
-                    p.out_f32, orow + c0 * esize);
-            if (TILE_N > 16 && nv > 16)
+            if (nv > 0) {
+              const int nvl = nv < 16 ? nv : 16;
+              int npad = (nvl + 7) & ~7;
+              if (k0 + c0 + npad > p.out_pitch) npad = nvl;
+              epi16(va, sbias + c0, *reinterpret_cast<const float(*)[16]>(&mk[c0]), p.act, p.slope, nvl, npad, p.out_f32,
+                    orow + c0 * esize);
+            }
+            if (TILE_N > 16 && nv > 16) {
+              const int nvl = nv < 32 ? nv - 16 : 16;
+              int npad = (nvl + 7) & ~7;
+              if (k0 + c0 + 16 + npad > p.out_pitch) npad = nvl;
               epi16(vb, sbias + c0 + 16, *reinterpret_cast<const float(*)[16]>(&mk[TILE_N > 16 ? c0 + 16 : 0]), p.act,
-                    p.slope, nv < 32 ? nv - 16 : 16, p.out_f32, orow + (c0 + 16) * esize);
+                    p.slope, nvl, npad, p.out_f32, orow + (c0 + 16) * esize);
+            }
           }
         }
       }
     }
+    if (p.tma_store && (int)threadIdx.x == 32 * (1 + WS_ISSUERS)) bulk_wait_all();
     if (dbg_on && threadIdx.x == 32 * (1 + WS_ISSUERS)) { p.dbg[5] = clock64() - t_begin; p.dbg[6] = w0; p.dbg[7] = w1; }
   }
   tc_fence_before();
@@ -315,7 +375,8 @@ int sm_count() {
 }
 
 template <int TILE_N, int KD>
-int launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, const WsParams& p, int grid, size_t smem, cudaStream_t st) {
+int launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const WsParams& p, int grid, size_t smem,
+              cudaStream_t st) {
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_ws_kernel<TILE_N, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -323,7 +384,7 @@ int launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, const WsParams& p, i
                 cudaGetErrorString(e));
     configured = smem;
   }
-  conv_ws_kernel<TILE_N, KD><<<(unsigned)grid, WS_THREADS, smem, st>>>(ma, mb, p);
+  conv_ws_kernel<TILE_N, KD><<<(unsigned)grid, WS_THREADS, smem, st>>>(ma, mb, mo, p);
   return icf::check_launch("conv_ws");
 }
 
@@ -416,6 +477,10 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
     const double cost = (1.0 / eff) * (1.0 + 0.25 * brange / xg);
     if (cost < best - 1e-9 || (cost < best + 1e-9 && xg > q.XG)) { best = cost; q.XG = xg; }
   }
+  {
+    static const int xg_env = []() { const char* e = getenv("ICF_WS_XG"); return e ? atoi(e) : 0; }();   // tuning aid
+    if (xg_env == 1 || xg_env == 2 || xg_env == 4 || xg_env == 8 || xg_env == 16) q.XG = xg_env;
+  }
   q.NG = 128 / q.XG;
   q.ng_shift = ilog2(q.NG);
   const int hx = q.XG + brange;
@@ -424,8 +489,9 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   q.sub_bytes = q.kc_bytes * (uint32_t)q.kchunks;
   q.slot_bytes = q.sub_bytes * (uint32_t)q.nsub;
   q.slab_bytes = (uint32_t)(max_ntaps * q.kchunks * tile_n) * 128u;
-  if ((int64_t)q.slab_bytes + 2 * (int64_t)q.slot_bytes > WS_SMEM_BUDGET) return -1;
-  q.n_slots = (int)((WS_SMEM_BUDGET - (int64_t)q.slab_bytes) / q.slot_bytes);
+  const int64_t stage_bytes = 2 * 128 * tile_n * 2;
+  if ((int64_t)q.slab_bytes + stage_bytes + 2 * (int64_t)q.slot_bytes > WS_SMEM_BUDGET) return -1;
+  q.n_slots = (int)((WS_SMEM_BUDGET - (int64_t)q.slab_bytes - stage_bytes) / q.slot_bytes);
   if (q.n_slots > WS_MAX_SLOTS) q.n_slots = WS_MAX_SLOTS;
   q.tiles_n = icf::cdiv(a->N, q.NG);
 
@@ -484,7 +550,25 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   }();
   q.dbg = dbg_buf;
 
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mo;
+  memset(&mo, 0, sizeof(mo));
+  // TMA-store epilogue: bf16 destination whose pixels are 16-byte aligned rows (pitch % 8 == 0)
+  q.tma_store = (!a->out_f32 && (a->out_pitch & 7) == 0 && (reinterpret_cast<uintptr_t>(a->dst) & 15) == 0) ? 1 : 0;
+  {
+    static const bool off = []() { const char* e = getenv("ICF_WS_NO_TMA_STORE"); return e && e[0] && e[0] != '0'; }();
+    if (off) q.tma_store = 0;
+  }
+  if (q.tma_store) {
+    int kp = (a->K + 7) & ~7;                       // ragged K: the pitch padding is written as zeros
+    if (kp > a->out_pitch) kp = a->K;
+    cuuint64_t dims[4] = {(cuuint64_t)kp, (cuuint64_t)a->N, (cuuint64_t)a->Q, (cuuint64_t)a->P};
+    cuuint64_t str[3] = {(cuuint64_t)a->P * a->Q * a->out_pitch * 2, (cuuint64_t)a->out_pitch * 2,
+                         (cuuint64_t)a->Q * a->out_pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)tile_n, (cuuint32_t)q.NG, (cuuint32_t)(q.XG * q.ostep), 1};
+    cuuint32_t est[4] = {1, 1, (cuuint32_t)q.ostep, 1};
+    const CUtensorMapSwizzle swz = tile_n == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (tile_n == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    if (int r = encode_map_swz(&mo, a->dst, 4, dims, str, box, est, swz)) return r;
+  }
   {
     cuuint64_t dims[4] = {(cuuint64_t)a->C, (cuuint64_t)a->N, (cuuint64_t)a->W, (cuuint64_t)a->H};
     cuuint64_t str[3] = {(cuuint64_t)a->H * a->W * a->in_pitch * 2, (cuuint64_t)a->in_pitch * 2,
@@ -501,17 +585,17 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
     if (int r = encode_map(&mb, a->w, 2, dims, str, box, est)) return r;
   }
   // shared memory: always more than half an SM's worth so that exactly one CTA (and one TMEM allocation) is resident
-  size_t smem = (size_t)q.slab_bytes + (size_t)q.n_slots * q.slot_bytes + 1024 + 1024;
+  size_t smem = (size_t)q.slab_bytes + (size_t)q.n_slots * q.slot_bytes + (size_t)stage_bytes + 1024 + 1024;
   if (smem < 120 * 1024) smem = 120 * 1024;
   int r;
   const int kd = q.kchunks == 1 ? q.kdepth_last : 0;
 #define ICF_WS_CASE(TN)                                                        \
   switch (kd) {                                                                \
-    case 1: r = launch_ws<TN, 1>(ma, mb, q, grid, smem, st); break;            \
-    case 2: r = launch_ws<TN, 2>(ma, mb, q, grid, smem, st); break;            \
-    case 3: r = launch_ws<TN, 3>(ma, mb, q, grid, smem, st); break;            \
-    case 4: r = launch_ws<TN, 4>(ma, mb, q, grid, smem, st); break;            \
-    default: r = launch_ws<TN, 0>(ma, mb, q, grid, smem, st); break;           \
+    case 1: r = launch_ws<TN, 1>(ma, mb, mo, q, grid, smem, st); break;            \
+    case 2: r = launch_ws<TN, 2>(ma, mb, mo, q, grid, smem, st); break;            \
+    case 3: r = launch_ws<TN, 3>(ma, mb, mo, q, grid, smem, st); break;            \
+    case 4: r = launch_ws<TN, 4>(ma, mb, mo, q, grid, smem, st); break;            \
+    default: r = launch_ws<TN, 0>(ma, mb, mo, q, grid, smem, st); break;           \
   }
   switch (tile_n) {
     case 16: ICF_WS_CASE(16) break;

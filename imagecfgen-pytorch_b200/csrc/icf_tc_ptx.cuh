@@ -196,6 +196,17 @@ inline EncodeTiledFn get_encode() {
   return fn;
 }
 
+inline int encode_map_swz(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                          const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode();
+  ICF_REQUIRE(fn, "tensor-core conv: cuTensorMapEncodeTiled is unavailable");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ICF_REQUIRE(r == CUDA_SUCCESS, "tensor-core conv: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
 inline int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box, const cuuint32_t* estr) {
   EncodeTiledFn fn = get_encode();

@@ -51,6 +51,8 @@ int icf_last_conv_path(void);
  * statistics of the result).
  *   dst[n,p,q,k] = mask[n,k] * act( bias[k] + sum_{r,s,c} src[n, y(p,r), x(q,s), c] * w[k][r*S+s][c] )
  * bf16: tcgen05.mma with TMEM accumulators, operands staged by TMA; f32: SIMT FMA.
+ * When K is not a multiple of 8 and out_pitch leaves room, the bf16 kernels also store zeros into the pitch
+ * padding dst[..., K .. roundup8(K)-1] (16-byte stores); that range must not alias live data.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct icf_conv_args {
   int32_t dtype;                 /* ICF_F32 | ICF_BF16: element type of src, w and (unless out_f32) dst */
