@@ -7,6 +7,7 @@
 
 int icf_simt_conv_forward(const icf_conv_args* a, cudaStream_t st);
 int icf_simt_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st);
+int icf_b1_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st);
 
 namespace icf {
 
@@ -99,7 +100,9 @@ int icf_conv_wgrad(const icf_wgrad_args* a, void* stream) {
   if (a->N == 0) return 0;
   cudaStream_t st = icf::as_stream(stream);
   if (a->dtype == ICF_BF16 && icf_tc_enabled()) {
-    int r = icf_tc_conv_wgrad(a, st);
+    int r = icf_b1_conv_wgrad(a, st);        // single-channel gradient operand: HBM-bound streaming reduction
+    if (r >= 0) return r;
+    r = icf_tc_conv_wgrad(a, st);
     if (r >= 0) return r;
   }
   ICF_REQUIRE(a->win <= 1, "icf_conv_wgrad: the folded (win) form exists only on the tensor-core path");

@@ -207,6 +207,90 @@ __global__ void __launch_bounds__(NT) wgrad_simt_kernel(const icf_wgrad_args a, 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient when `big` has ONE channel (the Cout = 1 last generator layer: small = X [N,P,Q,A],
+// big = dY [N,H,W,1]):   dw[a][r*S+s] += sum_{n,p,q} X[n,p,q,a] * dY[n, p*stride-pad+r, q*stride-pad+s]
+// A tensor-core tile would be 1/64 full; this is an HBM-bound streaming reduction instead: one block walks whole
+// images, keeps the image's dY plane in shared memory (broadcast reads), lane = channel pair, warp = pixel.
+// ------------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(256) wgrad_b1_kernel(const icf_wgrad_args a) {
+  extern __shared__ float sdy[];                   // [H*W] of the current image, then [8][KS*KS][64] reduction scratch
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int HW = a.H * a.W, PQ = a.P * a.Q;
+  const __nv_bfloat16* __restrict__ sm = reinterpret_cast<const __nv_bfloat16*>(a.small_t);
+  const __nv_bfloat16* __restrict__ bg = reinterpret_cast<const __nv_bfloat16*>(a.big_t);
+  for (int a0 = 0; a0 < a.A; a0 += 64) {           // 64 channels per pass (one bf16 pair per lane)
+    float acc[KS * KS][2];
+#pragma unroll
+    for (int t = 0; t < KS * KS; ++t) acc[t][0] = acc[t][1] = 0.f;
+    const int ch = a0 + 2 * lane;
+    for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < HW; i += blockDim.x) sdy[i] = __bfloat162float(bg[((int64_t)n * HW + i) * a.b_pitch]);
+      __syncthreads();
+      for (int pix = warp; pix < PQ; pix += 8) {
+        const int p = pix / a.Q, q = pix - p * a.Q;
+        float x0 = 0.f, x1 = 0.f;
+        if (ch + 1 < a.A) {
+          const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(sm + ((int64_t)n * PQ + pix) * a.a_pitch + ch);
+          x0 = __bfloat162float(v.x);
+          x1 = __bfloat162float(v.y);
+        } else if (ch < a.A) {
+          x0 = __bfloat162float(sm[((int64_t)n * PQ + pix) * a.a_pitch + ch]);
+        }
+        const int y0 = p * a.stride - a.pad, xx0 = q * a.stride - a.pad;
+#pragma unroll
+        for (int r = 0; r < KS; ++r) {
+          const int y = y0 + r;
+          const bool yin = y >= 0 && y < a.H;
+#pragma unroll
+          for (int c = 0; c < KS; ++c) {
+            const int x = xx0 + c;
+            const float v = (yin && x >= 0 && x < a.W) ? sdy[y * a.W + x] : 0.f;
+            acc[r * KS + c][0] = fmaf(x0, v, acc[r * KS + c][0]);
+            acc[r * KS + c][1] = fmaf(x1, v, acc[r * KS + c][1]);
+          }
+        }
+      }
+    }
+    // cross-warp reduction, then one atomic per (channel, tap) and block
+    __syncthreads();
+    float* red = sdy + HW;
+#pragma unroll
+    for (int t = 0; t < KS * KS; ++t) {
+      red[(warp * KS * KS + t) * 64 + 2 * lane] = acc[t][0];
+      red[(warp * KS * KS + t) * 64 + 2 * lane + 1] = acc[t][1];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < KS * KS * 64; i += blockDim.x) {
+      const int t = i / 64, c = i - t * 64;
+      if (a0 + c >= a.A) continue;
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += red[(w * KS * KS + t) * 64 + c];
+      atomicAdd(a.dw + ((int64_t)(a0 + c) * KS * KS + t) * a.B, v);
+    }
+  }
+}
+
+template <int KS>
+int launch_wgrad_b1(const icf_wgrad_args* a, cudaStream_t st) {
+  const size_t smem = ((size_t)a->H * a->W + 8 * KS * KS * 64) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    if (cudaFuncSetAttribute(wgrad_b1_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return -1;
+    }
+    configured = smem;
+  }
+  int grid = a->N < 148 * 4 ? a->N : 148 * 4;
+  wgrad_b1_kernel<KS><<<grid, 256, smem, st>>>(*a);
+  return icf::check_launch("wgrad_b1");
+}
+
 template <typename T, int FORM>
 int launch_conv(const icf_conv_args* a, cudaStream_t st) {
   const int64_t M = (int64_t)a->N * a->P * a->Q;
@@ -244,4 +328,17 @@ int icf_simt_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
   if (a->dtype == ICF_F32) wgrad_simt_kernel<float><<<grid, NT, 0, st>>>(*a, splits, pps);
   else wgrad_simt_kernel<__nv_bfloat16><<<grid, NT, 0, st>>>(*a, splits, pps);
   return icf::check_launch("wgrad_simt");
+}
+
+// single-channel `big` operand (bf16): streaming reduction kernel; -1 = not applicable
+int icf_b1_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
+  if (a->dtype != ICF_BF16 || a->B != 1 || a->win > 1 || a->R != a->S || (a->a_pitch & 1)) return -1;
+  if ((reinterpret_cast<uintptr_t>(a->small_t) & 3) != 0) return -1;
+  if (((size_t)a->H * a->W + 8 * 25 * 64) * sizeof(float) > 200 * 1024) return -1;
+  switch (a->R) {
+    case 3: return launch_wgrad_b1<3>(a, st);
+    case 4: return launch_wgrad_b1<4>(a, st);
+    case 5: return launch_wgrad_b1<5>(a, st);
+    default: return -1;
+  }
 }

@@ -96,6 +96,30 @@ __global__ void imgfeat_bwd_kernel(const icf_imgfeat_args a) {
   }
 }
 
+// same gradient, one THREAD per (sample, plane, cell): for small images (28x28: 1-4 pixels per cell) a warp per
+// cell would leave 28+ lanes idle
+__global__ void imgfeat_bwd_small_kernel(const icf_imgfeat_args a) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)a.N * a.n_emb * 256;
+  if (t >= total) return;
+  const int cell = (int)(t & 255);
+  const int e = (int)((t >> 8) % a.n_emb);
+  const int n = (int)((t >> 8) / a.n_emb);
+  const int cy = cell >> 4, cx = cell & 15;
+  const int y0 = (cy * a.H + 15) / 16, y1 = ((cy + 1) * a.H + 15) / 16;
+  const int x0 = (cx * a.W + 15) / 16, x1 = ((cx + 1) * a.W + 15) / 16;
+  const int ch = 1 + e;
+  float sum = 0.f;
+  for (int y = y0; y < y1; ++y)
+    for (int x = x0; x < x1; ++x)
+      sum += icf::ld_any(a.dfeat, a.dtype, (((int64_t)n * a.H + y) * a.W + x) * a.feat_pitch + ch);
+  const int idx = a.emb_index[e][n];
+  const float tv = tanhf(a.emb_table[e][(int64_t)idx * 256 + cell]);
+  float g = sum * (1.f - tv * tv);
+  if (a.mask) g *= a.mask[(int64_t)n * a.mask_pitch + ch];
+  if (g != 0.f) atomicAdd(a.demb_table[e] + (int64_t)idx * 256 + cell, g);
+}
+
 // ------------------------------------------------------------------------------------------------
 // latent feature vector: [z | onehot_i @ table_i ... | cont ... | 0 pad]
 // ------------------------------------------------------------------------------------------------
@@ -163,17 +187,20 @@ __global__ void latfeat_bwd_rows_kernel(const icf_latfeat_args a) {
 }
 
 // d_table[e][k][col] += sum_n onehot[n][k] * dfeat[n][latent + e*256 + col]; block per (e,k), thread per col
+// the sample range is split over blockIdx.y (a serial loop over the whole batch is latency-bound)
 __global__ void latfeat_bwd_table_kernel(const icf_latfeat_args a, int e) {
   const int k = blockIdx.x;
   const int col = threadIdx.x;   // 256 threads
   const int K = a.emb_k[e];
+  const int per = (a.N + gridDim.y - 1) / gridDim.y;
+  const int n_lo = blockIdx.y * per, n_hi = min(a.N, n_lo + per);
   float s = 0.f;
-  for (int n = 0; n < a.N; ++n) {
+  for (int n = n_lo; n < n_hi; ++n) {
     const float oh = a.onehot[e][(int64_t)n * K + k];
     if (oh != 0.f)
       s = fmaf(oh, icf::ld_any(a.dfeat, a.dtype, (int64_t)n * a.feat_pitch + a.latent + e * 256 + col), s);
   }
-  a.demb_table[e][(int64_t)k * 256 + col] += s;
+  if (s != 0.f) atomicAdd(a.demb_table[e] + (int64_t)k * 256 + col, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -246,6 +273,30 @@ __global__ void bn_bwd_reduce_kernel(const void* dU, int ddt, int dpitch, const 
     for (int k = 0; k < 8; ++k) { t0 += red[0][k][cx]; t1 += red[1][k][cx]; }
     atomicAdd(sums + c, t0);
     atomicAdd(sums + C + c, t1);
+  }
+}
+
+// few-channel variant (C <= 4, no BatchNorm): one thread per pixel, block-reduced bias gradient — the 32-channel-lane
+// kernel below would run one lane in 32 for the single-channel image gradient of the last generator layer
+__global__ void act_backward_fewc_kernel(const icf_actbwd_args a) {
+  __shared__ float red[32];
+  float sb[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < a.pixels; pix += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = pix / a.pixels_per_sample;
+    for (int c = 0; c < a.C; ++c) {
+      float g = icf::ld_any(a.dOut, a.d_dtype, pix * a.d_pitch + c);
+      const float yv = icf::ld_any(a.y, a.y_dtype, pix * a.y_pitch + c);
+      if (a.out_mask) g *= a.out_mask[n * a.mask_pitch + c];
+      g *= icf::act_grad_from_output(yv, a.act, a.slope);
+      icf::st_any(a.dPre, a.p_dtype, pix * a.p_pitch + c, g);
+      sb[c] += g;
+    }
+  }
+  if (a.dbias) {
+    for (int c = 0; c < a.C; ++c) {
+      const float t = icf::block_sum(sb[c], red);
+      if (threadIdx.x == 0) atomicAdd(a.dbias + (a.bias_mod > 0 ? c % a.bias_mod : c), t);
+    }
   }
 }
 
@@ -714,6 +765,10 @@ int icf_image_features_bwd(const icf_imgfeat_args* a, void* stream) {
   ICF_REQUIRE(a && a->dfeat, "icf_image_features_bwd: null pointer");
   if (a->n_emb == 0 || a->N == 0) return 0;
   const int64_t warps = (int64_t)a->N * a->n_emb * 256;
+  if (icf::cdiv(a->H, 16) * icf::cdiv(a->W, 16) <= 8) {      // a handful of pixels per embedding cell
+    imgfeat_bwd_small_kernel<<<icf::cdiv(warps, EW_THREADS), EW_THREADS, 0, icf::as_stream(stream)>>>(*a);
+    return icf::check_launch("imgfeat_bwd_small");
+  }
   imgfeat_bwd_kernel<<<icf::cdiv(warps * 32, EW_THREADS), EW_THREADS, 0, icf::as_stream(stream)>>>(*a);
   return icf::check_launch("imgfeat_bwd");
 }
@@ -744,7 +799,7 @@ int icf_latent_features_bwd(const icf_latfeat_args* a, void* stream) {
   }
   for (int e = 0; e < a->n_emb; ++e) {
     if (!a->demb_table[e]) continue;
-    latfeat_bwd_table_kernel<<<a->emb_k[e], 256, 0, st>>>(*a, e);
+    latfeat_bwd_table_kernel<<<dim3(a->emb_k[e], icf::cdiv(a->N, 64)), 256, 0, st>>>(*a, e);
     if (int r = icf::check_launch("latfeat_bwd_table")) return r;
   }
   return 0;
@@ -814,6 +869,12 @@ int icf_act_backward(const icf_actbwd_args* a, void* stream) {
       act_backward_v8<<<vgrid(a->C, a->pixels), VT, 0, icf::as_stream(stream)>>>(*a);
       return icf::check_launch("act_backward_v8");
     }
+  }
+  if (a->C <= 4 && !a->bn_sums) {
+    int64_t blocks = (a->pixels + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    act_backward_fewc_kernel<<<(unsigned)blocks, 256, 0, icf::as_stream(stream)>>>(*a);
+    return icf::check_launch("act_backward_fewc");
   }
   const int groups = icf::cdiv(a->C, 32);
   dim3 grid(groups, pixel_slabs(a->pixels, groups));

@@ -111,7 +111,9 @@ def test_conv_transposed(case, code):
 
 
 WGRAD_CASES = [(3, 5, 28, 64, 3, 2, 1), (2, 64, 14, 128, 4, 2, 1), (9, 256, 3, 512, 4, 2, 1), (4, 32, 24, 64, 4, 2, 0),
-               (33, 512, 1, 512, 1, 1, 0), (2, 7, 32, 64, 5, 2, 1)]
+               (33, 512, 1, 512, 1, 1, 0), (2, 7, 32, 64, 5, 2, 1),
+               # single-channel gradient operand (Cout = 1 generator tail): streaming-reduction kernel
+               (6, 1, 28, 64, 4, 1, 0), (3, 1, 20, 40, 5, 2, 2), (2, 1, 12, 130, 3, 1, 1)]
 
 
 @pytest.mark.parametrize("code", [0, 1], ids=["fp32", "bf16"])
