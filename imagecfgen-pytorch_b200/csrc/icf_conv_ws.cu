@@ -63,6 +63,8 @@ struct WsParams {
   int sstep, ostep, n_classes;
   int XG, NG, ng_shift;
   int kchunks, kdepth_last, w_pitch;
+  int rowb;                    // bytes per operand row in shared memory: 128 (64-channel K chunk, 128B swizzle) or
+                               // 64 (C <= 32: 32-channel chunk, 64B swizzle — half the staging traffic and footprint)
   int nsub, n_slots, n_acc, acc_shift;
   int tiles_n, tiles_k;
   uint32_t slot_bytes, sub_bytes, kc_bytes, slab_bytes, tmem_cols;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
   long long w0 = 0, w1 = 0;                 // cycles spent in this role's two kinds of barrier waits
   const long long t_begin = dbg_on ? clock64() : 0;
-  constexpr uint32_t W_BLOCK = TILE_N * 128;      // one (tap, K chunk) block of the weight slab
+  const uint32_t W_BLOCK = (uint32_t)TILE_N * (uint32_t)p.rowb;      // one (tap, K chunk) block of the weight slab
 
   if (warp == 0) {
     // ===== TMA producer: weight slab once, then the source rows of every column =====
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
       for (int t = 0; t < cl.ntaps; ++t)
         for (int kc = 0; kc < p.kchunks; ++kc)
           tma_load_2d(slab_addr + (uint32_t)(t * p.kchunks + kc) * W_BLOCK, &map_b, w_full,
-                      cl.taps[t].widx * p.w_pitch + kc * 64, k0);
+                      cl.taps[t].widx * p.w_pitch + kc * (p.rowb >> 1), k0);
       int s = 0;
       uint32_t ph = 0;
       for (int col = r0; col < ncols; col += rstep) {
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
           const uint32_t base = slots_addr + (uint32_t)s * p.slot_bytes;
           for (int sub = 0; sub < p.nsub; ++sub)
             for (int kc = 0; kc < p.kchunks; ++kc)
-              tma_load_4d(base + sub * p.sub_bytes + kc * p.kc_bytes, &map_a, slot_full(s), kc * 64, n0,
+              tma_load_4d(base + sub * p.sub_bytes + kc * p.kc_bytes, &map_a, slot_full(s), kc * (p.rowb >> 1), n0,
                           xs + cl.x0[sub], y);
           if (++s == p.n_slots) { s = 0; ph ^= 1; }
         }
@@ -176,12 +178,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     // ===== MMA issuers: whole warp runs the control flow, one elected lane issues.  Issuer wi owns the output rows
     // i with i % WS_ISSUERS == wi, so all MMAs into one accumulator come from one thread (ordered). =====
     constexpr uint32_t idesc = make_idesc(128, TILE_N, 0, 0);
-    constexpr uint32_t WB16 = W_BLOCK >> 4;
+    const uint32_t WB16 = W_BLOCK >> 4;
     const int wi = warp - 1;
     const uint32_t leader = elect_one();
     mbar_wait(w_full, 0);
     tc_fence_after();
-    const uint64_t d0 = make_desc(0, 16, 1024);
+    const uint64_t d0 = make_desc_sw(0, 16, 8u * (uint32_t)p.rowb, p.rowb == 64 ? 4u : 2u);
     const uint32_t desc_hi = (uint32_t)(d0 >> 32), lbo_lo = (uint32_t)d0;     // low word without an address
     const uint32_t b_lo0 = ((slab_addr >> 4) & 0x3FFFu) | lbo_lo;
     const uint32_t kc16 = p.kc_bytes >> 4;
@@ -408,6 +410,7 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   q.n_classes = q.ostep * q.ostep;
   q.kchunks = icf::cdiv(a->C, 64);
   q.kdepth_last = icf::cdiv(a->C - 64 * (q.kchunks - 1), 16);
+  q.rowb = a->C <= 32 ? 64 : 128;
   q.w_pitch = a->w_pitch;
   const int tile_n = a->K <= 16 ? 16 : (a->K <= 32 ? 32 : 64);
   q.tiles_k = icf::cdiv(a->K, tile_n);
@@ -485,10 +488,10 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   q.ng_shift = ilog2(q.NG);
   const int hx = q.XG + brange;
   if (hx * q.sstep > 256) return -1;
-  q.kc_bytes = (uint32_t)(hx * q.NG) * 128u;
+  q.kc_bytes = (uint32_t)(hx * q.NG) * (uint32_t)q.rowb;
   q.sub_bytes = q.kc_bytes * (uint32_t)q.kchunks;
   q.slot_bytes = q.sub_bytes * (uint32_t)q.nsub;
-  q.slab_bytes = (uint32_t)(max_ntaps * q.kchunks * tile_n) * 128u;
+  q.slab_bytes = ((uint32_t)(max_ntaps * q.kchunks * tile_n) * (uint32_t)q.rowb + 1023u) & ~1023u;
   const int64_t stage_bytes = 2 * 128 * tile_n * 2;
   if ((int64_t)q.slab_bytes + stage_bytes + 2 * (int64_t)q.slot_bytes > WS_SMEM_BUDGET) return -1;
   q.n_slots = (int)((WS_SMEM_BUDGET - (int64_t)q.slab_bytes - stage_bytes) / q.slot_bytes);
@@ -505,7 +508,7 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
       const int par = ((dx % q.sstep) + q.sstep) % q.sstep, b = floor_div(dx, q.sstep);
       cl.taps[t].dy = (int16_t)raw[c][t].dy;
       cl.taps[t].widx = (int16_t)raw[c][t].widx;
-      cl.taps[t].a_off16 = ((uint32_t)sub_index[par] * q.sub_bytes + (uint32_t)((b - bmin[par]) * q.NG) * 128u) >> 4;
+      cl.taps[t].a_off16 = ((uint32_t)sub_index[par] * q.sub_bytes + (uint32_t)((b - bmin[par]) * q.NG) * (uint32_t)q.rowb) >> 4;
       if (t == 0 || raw[c][t].dy != raw[c][t - 1].dy) {
         if (cl.ngroups == WS_MAX_GROUPS) return -1;
         cl.grp[cl.ngroups].dy = (int16_t)raw[c][t].dy;
@@ -573,16 +576,16 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
     cuuint64_t dims[4] = {(cuuint64_t)a->C, (cuuint64_t)a->N, (cuuint64_t)a->W, (cuuint64_t)a->H};
     cuuint64_t str[3] = {(cuuint64_t)a->H * a->W * a->in_pitch * 2, (cuuint64_t)a->in_pitch * 2,
                          (cuuint64_t)a->W * a->in_pitch * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)q.NG, (cuuint32_t)(hx * q.sstep), 1};
+    cuuint32_t box[4] = {(cuuint32_t)(q.rowb / 2), (cuuint32_t)q.NG, (cuuint32_t)(hx * q.sstep), 1};
     cuuint32_t est[4] = {1, 1, (cuuint32_t)q.sstep, 1};
-    if (int r = encode_map(&ma, a->src, 4, dims, str, box, est)) return r;
+    if (int r = encode_map_swz(&ma, a->src, 4, dims, str, box, est, q.rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B)) return r;
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)taps_all * a->w_pitch, (cuuint64_t)a->w_rows};
     cuuint64_t str[1] = {(cuuint64_t)taps_all * a->w_pitch * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)tile_n};
+    cuuint32_t box[2] = {(cuuint32_t)(q.rowb / 2), (cuuint32_t)tile_n};
     cuuint32_t est[2] = {1, 1};
-    if (int r = encode_map(&mb, a->w, 2, dims, str, box, est)) return r;
+    if (int r = encode_map_swz(&mb, a->w, 2, dims, str, box, est, q.rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B)) return r;
   }
   // shared memory: always more than half an SM's worth so that exactly one CTA (and one TMEM allocation) is resident
   size_t smem = (size_t)q.slab_bytes + (size_t)q.n_slots * q.slot_bytes + (size_t)stage_bytes + 1024 + 1024;

@@ -167,6 +167,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)2 << 61;   // SWIZZLE_128B
   return d;
 }
+// same with an explicit swizzle code in bits 61..63 (2 = 128B, 4 = 64B, 6 = 32B); SBO = 8 rows of that width
+__device__ __forceinline__ uint64_t make_desc_sw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout & 7u) << 61;
+  return d;
+}
 // instruction descriptor: D fp32, A/B bf16, M x N tile, operand majors (0 = K-major, 1 = MN-major)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |

@@ -111,6 +111,16 @@ class LayerExec:
             self.perm_g = ops.make_perm(hw, cu, C_, C_, hw * C_, 1)              # dw packed [hw*cu][C]
             self.perm_bias = ops.make_perm(1, hw, cu, 0, 1, hw)
         self.wgrad_elems = self.Kout * self.taps * self.Cin
+        # ConvTranspose2d on a 1x1 input (stride 1, no padding): output pixel (p, q) sees exactly tap (p, q), so the
+        # forward is a plain GEMM [N, Cin] x [Cin, taps*Cout] whose output row is already the NHWC [k, k, Cout] image;
+        # the transposed-conv form would push all taps through every output pixel (taps-1 of them multiplying zeros)
+        self.gemm_fwd = (spec.kind == "convT" and hin == 1 and win == 1 and spec.pad == 0 and spec.opad == 0
+                         and self.P == spec.k and self.Q == spec.k)
+        if self.gemm_fwd:
+            self.w_gemm = torch.zeros(self.taps * K_ * self.wf_pitch, dtype=dt, device=device)
+            self.perm_gemm = ops.make_perm(self.taps, K_, C_, 1, self.taps, K_ * self.taps, d2_pad=self.wf_pitch)
+            self.bias_gemm = torch.zeros(self.taps * K_, dtype=torch.float32, device=device)
+            self.perm_bias_gemm = ops.make_perm(1, self.taps, K_, 0, 0, 1)
         # folded form of a small-channel first conv (bf16 tensor-core path): the S filter columns become part of
         # the channel dimension of a pre-padded 8-channel input, cutting the K loop from R*S taps to R rows
         if fold and spec.kind == "conv" and code == BF16 and pad8(self.Cin) == 8 and self.S * 8 <= 64 and self.S > 1:
@@ -133,6 +143,9 @@ class LayerExec:
             ops.cast(bias.data_ptr(), F32, self.bias.data_ptr(), F32, self.Kout)
         else:
             ops.pack(bias.data_ptr(), self.bias.data_ptr(), F32, self.perm_bias)
+        if self.gemm_fwd:
+            ops.pack(weight.data_ptr(), self.w_gemm.data_ptr(), self.code, self.perm_gemm)
+            ops.pack(bias.data_ptr(), self.bias_gemm.data_ptr(), F32, self.perm_bias_gemm)
 
     # ---- launches -------------------------------------------------------------------------------
     def forward(self, N, x: Act, y: Act, mask=None, mask_pitch=0, stats=None, out_f32=False):
@@ -143,6 +156,12 @@ class LayerExec:
                              x.ptr, self.w_fold.data_ptr(), self.Kout, self.fold_pitch, y.ptr, bias=self.bias.data_ptr(),
                              act=sp.act, slope=sp.slope, out_f32=out_f32, mask=mask, mask_pitch=mask_pitch, stats=stats,
                              win=self.fold, alg_flops=self.alg_flops_img * N)
+            return
+        if self.gemm_fwd and mask is None and stats is None and y.pitch == self.Kout and y.off == 0:
+            ops.conv_forward(self.code, ops.GATHER, N, 1, 1, self.Cin, x.pitch, 1, 1, self.taps * self.Kout,
+                             y.pitch * self.taps, 1, 1, 1, 0, x.ptr, self.w_gemm.data_ptr(), self.taps * self.Kout,
+                             self.wf_pitch, y.ptr, bias=self.bias_gemm.data_ptr(), act=sp.act, slope=sp.slope,
+                             out_f32=out_f32, alg_flops=self.alg_flops_img * N)
             return
         ops.conv_forward(self.code, self.form, N, self.Hin, self.Win, self.Cin, x.pitch,
                          self.P, self.Q, self.Kout, y.pitch if sp.kind != "linear" else y.pitch * self.Hout * self.Wout,
