@@ -4,6 +4,12 @@
 
 namespace {
 
+// sample index of a pixel: 32-bit unsigned division whenever the pixel index fits (a 64-bit division costs ~10x
+// more issue slots than the rest of a 16-byte-per-thread streaming iteration)
+__device__ __forceinline__ int64_t sample_of(int64_t pix, int pps) {
+  return pix <= 0xffffffffLL ? (int64_t)((uint32_t)pix / (uint32_t)pps) : pix / pps;
+}
+
 constexpr int EW_THREADS = 256;
 
 // ------------------------------------------------------------------------------------------------
@@ -241,7 +247,7 @@ __global__ void scale_shift_mask_kernel(const void* y, int ydt, int ypitch, void
     const int c = (int)(i - pix * C);
     float v = icf::ld_any(y, ydt, pix * ypitch + c);
     if (scale) v = fmaf(v, scale[c], shift ? shift[c] : 0.f);
-    if (mask) v *= mask[(pix / pps) * mpitch + c];
+    if (mask) v *= mask[sample_of(pix, pps) * mpitch + c];
     icf::st_any(u, udt, pix * upitch + c, v);
   }
 }
@@ -258,7 +264,7 @@ __global__ void bn_bwd_reduce_kernel(const void* dU, int ddt, int dpitch, const 
     const float mu = mean[c], is = invstd[c];
     for (int64_t pix = (int64_t)blockIdx.y * 8 + py; pix < pixels; pix += (int64_t)gridDim.y * 8) {
       float g = icf::ld_any(dU, ddt, pix * dpitch + c);
-      if (mask) g *= mask[(pix / pps) * mpitch + c];
+      if (mask) g *= mask[sample_of(pix, pps) * mpitch + c];
       const float xh = (icf::ld_any(y, ydt, pix * ypitch + c) - mu) * is;
       s0 += g;
       s1 = fmaf(g, xh, s1);
@@ -282,7 +288,7 @@ __global__ void act_backward_fewc_kernel(const icf_actbwd_args a) {
   __shared__ float red[32];
   float sb[4] = {0.f, 0.f, 0.f, 0.f};
   for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < a.pixels; pix += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t n = pix / a.pixels_per_sample;
+    const int64_t n = sample_of(pix, a.pixels_per_sample);
     for (int c = 0; c < a.C; ++c) {
       float g = icf::ld_any(a.dOut, a.d_dtype, pix * a.d_pitch + c);
       const float yv = icf::ld_any(a.y, a.y_dtype, pix * a.y_pitch + c);
@@ -322,7 +328,7 @@ __global__ void act_backward_kernel(const icf_actbwd_args a) {
       }
     }
     for (int64_t pix = (int64_t)blockIdx.y * 8 + py; pix < a.pixels; pix += (int64_t)gridDim.y * 8) {
-      const int64_t n = pix / a.pixels_per_sample;
+      const int64_t n = sample_of(pix, a.pixels_per_sample);
       float g = icf::ld_any(a.dOut, a.d_dtype, pix * a.d_pitch + c);
       const float yv = icf::ld_any(a.y, a.y_dtype, pix * a.y_pitch + c);
       if (bn) {
@@ -462,7 +468,7 @@ __global__ void __launch_bounds__(VT) scale_shift_mask_v8(const void* y, int ydt
       for (int j = 0; j < 8; ++j) v.v[j] = fmaf(v.v[j], sc.v[j], sh.v[j]);
     }
     if (mask) {
-      const V8 mk = ldf8(mask + (pix / pps) * mpitch + m.c0);
+      const V8 mk = ldf8(mask + sample_of(pix, pps) * mpitch + m.c0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v.v[j] *= mk.v[j];
     }
@@ -484,7 +490,7 @@ __global__ void __launch_bounds__(VT) bn_bwd_reduce_v8(const void* dU, int ddt, 
       V8 g = ld8(dU, ddt, pix * dpitch + m.c0);
       const V8 yv = ld8(y, ydt, pix * ypitch + m.c0);
       if (mask) {
-        const V8 mk = ldf8(mask + (pix / pps) * mpitch + m.c0);
+        const V8 mk = ldf8(mask + sample_of(pix, pps) * mpitch + m.c0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) g.v[j] *= mk.v[j];
       }
@@ -541,7 +547,7 @@ __global__ void __launch_bounds__(VT) act_backward_v8(const icf_actbwd_args a) {
       }
     }
     for (int64_t pix = m.pix0; pix < a.pixels; pix += m.pstride) {
-      const int64_t n = pix / a.pixels_per_sample;
+      const int64_t n = sample_of(pix, a.pixels_per_sample);
       V8 g = ld8(a.dOut, a.d_dtype, pix * a.d_pitch + m.c0);
       const V8 yv = ld8(a.y, a.y_dtype, pix * a.y_pitch + m.c0);
       if (bn) {

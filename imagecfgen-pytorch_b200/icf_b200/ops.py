@@ -200,14 +200,18 @@ def bn_finalize(stats, Cc, count, gamma, beta, eps, momentum, rmean, rvar, nbt, 
 
 def scale_shift_mask(y, y_dtype, y_pitch, u, u_dtype, u_pitch, pixels, pixels_per_sample, Cc, scale=None,
                      shift=None, mask=None, mask_pitch=0):
+    es = lambda d: 4 if d == F32 else 2
     _launch("icf_scale_shift_mask", _l.load().icf_scale_shift_mask, y, y_dtype, y_pitch, u, u_dtype, u_pitch, pixels, pixels_per_sample, Cc,
-                                    scale, shift, mask, mask_pitch)
+                                    scale, shift, mask, mask_pitch, nbytes=float(pixels) * Cc * (es(y_dtype) + es(u_dtype)),
+            detail=f"scale_shift_mask C{Cc} pix{pixels}" if PROFILE is not None else "")
 
 
 def bn_bwd_reduce(dU, d_dtype, d_pitch, y, y_dtype, y_pitch, pixels, pps, Cc, mask, mask_pitch, mean, invstd,
                   sums):
+    es = lambda d: 4 if d == F32 else 2
     _launch("icf_bn_bwd_reduce", _l.load().icf_bn_bwd_reduce, dU, d_dtype, d_pitch, y, y_dtype, y_pitch, pixels, pps, Cc, mask, mask_pitch,
-                                 mean, invstd, sums)
+                                 mean, invstd, sums, nbytes=float(pixels) * Cc * (es(d_dtype) + es(y_dtype)),
+            detail=f"bn_bwd_reduce C{Cc} pix{pixels}" if PROFILE is not None else "")
 
 
 def act_backward(dOut, d_dtype, d_pitch, y, y_dtype, y_pitch, dPre, p_dtype, p_pitch, pixels, pps, Cc, act,
@@ -216,7 +220,10 @@ def act_backward(dOut, d_dtype, d_pitch, y, y_dtype, y_pitch, dPre, p_dtype, p_p
     a = _l.ActBwdArgs(d_dtype, d_pitch, y_dtype, y_pitch, p_dtype, p_pitch, pixels, pps, Cc, ACT[act], slope,
                       mask_pitch, bn_mask_pitch, dOut, y, dPre, out_mask, dbias, 0, bn_sums, bn_mask, bn_gamma,
                       bn_mean, bn_invstd, bn_dgamma, bn_dbeta)
-    _launch("icf_act_backward", _l.load().icf_act_backward, C.byref(a))
+    es = lambda d: 4 if d == F32 else 2
+    _launch("icf_act_backward", _l.load().icf_act_backward, C.byref(a),
+            nbytes=float(pixels) * Cc * (es(d_dtype) + es(y_dtype) + es(p_dtype)),
+            detail=(f"act_backward C{Cc} pix{pixels}" + (" bn" if bn_sums else "")) if PROFILE is not None else "")
 
 
 def bce_logits(logits, l_dtype, l_pitch, n, target, weight, loss_out, dlogits, d_dtype, d_pitch):
