@@ -50,26 +50,50 @@ __global__ void imgfeat_fwd_kernel(const icf_imgfeat_args a) {
   const int n = (int)(o / hwp);
   const int remp = (int)(o - (int64_t)n * hwp);
   const int y = remp / Wp - a.pad, x = remp % Wp - a.pad;
-  if (y < 0 || y >= a.H || x < 0 || x >= a.W) {                        // zero border
+  const bool vec = a.dtype == ICF_BF16 && a.feat_pitch == 8;           // one 16-byte store per pixel
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = 0.f;
+  const bool inside = y >= 0 && y < a.H && x >= 0 && x < a.W;
+  if (!inside && !vec) {                                               // zero border
     for (int ch = 0; ch < a.feat_pitch; ++ch) icf::st_any(a.feat, a.dtype, o * a.feat_pitch + ch, 0.f);
     return;
   }
-  const int64_t i = ((int64_t)n * a.H + y) * a.W + x;                  // source pixel
-  const int cy = min((y * 16) / a.H, 15), cx = min((x * 16) / a.W, 15);   // nearest: floor(dst*16/size)
-  const float* mk = a.mask ? a.mask + (int64_t)n * a.mask_pitch : nullptr;
-  int ch = 0;
-  float v = icf::ld_any(a.x, a.x_dtype, i * a.x_pitch);
-  icf::st_any(a.feat, a.dtype, o * a.feat_pitch + ch, mk ? v * mk[ch] : v);
-  ++ch;
-  for (int e = 0; e < a.n_emb; ++e, ++ch) {
-    const float t = tanhf(a.emb_table[e][(int64_t)a.emb_index[e][n] * 256 + cy * 16 + cx]);
-    icf::st_any(a.feat, a.dtype, o * a.feat_pitch + ch, mk ? t * mk[ch] : t);
+  if (inside) {
+    const int64_t i = ((int64_t)n * a.H + y) * a.W + x;                  // source pixel
+    const int cy = min((y * 16) / a.H, 15), cx = min((x * 16) / a.W, 15);   // nearest: floor(dst*16/size)
+    const float* mk = a.mask ? a.mask + (int64_t)n * a.mask_pitch : nullptr;
+    int ch = 0;
+    const float v = icf::ld_any(a.x, a.x_dtype, i * a.x_pitch);
+    f[0] = mk ? v * mk[0] : v;
+    ++ch;
+#pragma unroll
+    for (int e = 0; e < ICF_MAX_PLANES - 1; ++e) {
+      if (e < a.n_emb) {
+        const float t = tanhf(a.emb_table[e][(int64_t)a.emb_index[e][n] * 256 + cy * 16 + cx]);
+        if (ch < 8) f[ch] = mk ? t * mk[ch] : t;
+        ++ch;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < ICF_MAX_PLANES - 1; ++e) {
+      if (e < a.n_cont) {
+        const float t = a.cont[e][n];
+        if (ch < 8) f[ch] = mk ? t * mk[ch] : t;
+        ++ch;
+      }
+    }
   }
-  for (int e = 0; e < a.n_cont; ++e, ++ch) {
-    const float t = a.cont[e][n];
-    icf::st_any(a.feat, a.dtype, o * a.feat_pitch + ch, mk ? t * mk[ch] : t);
+  if (vec) {
+    uint4 w;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
+    w.x = *reinterpret_cast<uint32_t*>(&p0); w.y = *reinterpret_cast<uint32_t*>(&p1);
+    w.z = *reinterpret_cast<uint32_t*>(&p2); w.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.feat) + o * 8) = w;
+  } else {
+    for (int ch = 0; ch < a.feat_pitch; ++ch) icf::st_any(a.feat, a.dtype, o * a.feat_pitch + ch, ch < 8 ? f[ch] : 0.f);
   }
-  for (; ch < a.feat_pitch; ++ch) icf::st_any(a.feat, a.dtype, o * a.feat_pitch + ch, 0.f);
 }
 
 // gradient into the embedding tables: one warp per (sample, plane, cell): reduce the cell's pixel block
@@ -758,9 +782,9 @@ int icf_argmax_rows(const void* x, int32_t x_dtype, int32_t n, int32_t k, int32_
 int icf_image_features_fwd(const icf_imgfeat_args* a, void* stream) {
   ICF_REQUIRE(a && a->x && a->feat, "icf_image_features_fwd: null pointer");
   ICF_REQUIRE(a->n_emb >= 0 && a->n_cont >= 0 && a->n_emb <= ICF_MAX_PLANES && a->n_cont <= ICF_MAX_PLANES &&
-                  1 + a->n_emb + a->n_cont <= a->feat_pitch,
-              "icf_image_features_fwd: %d emb + %d cont planes do not fit pitch %d", a->n_emb, a->n_cont,
-              a->feat_pitch);
+                  1 + a->n_emb + a->n_cont <= a->feat_pitch && 1 + a->n_emb + a->n_cont <= 8,
+              "icf_image_features_fwd: %d emb + %d cont planes do not fit pitch %d (at most 8 feature channels)", a->n_emb,
+              a->n_cont, a->feat_pitch);
   const int64_t total = (int64_t)a->N * (a->H + 2 * a->pad) * (a->W + 2 * a->pad);
   if (total == 0) return 0;
   imgfeat_fwd_kernel<<<icf::cdiv(total, EW_THREADS), EW_THREADS, 0, icf::as_stream(stream)>>>(*a);
