@@ -403,6 +403,21 @@ __device__ __forceinline__ V8 ld8(const void* base, int dtype, int64_t idx) {
   }
   return r;
 }
+__device__ __forceinline__ V8 cvt8(const uint4& u) {          // 8 packed bf16 -> fp32
+  V8 r;
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r.v[2 * i] = __uint_as_float(w[i] << 16);
+    r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+  return r;
+}
+__device__ __forceinline__ uint4 ldraw8(const void* base, int64_t idx) {
+  return __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx));
+}
+constexpr int VU = 4;            // pixels in flight per thread in the bf16 streaming loops (memory-level parallelism)
+
 __device__ __forceinline__ void st8(void* base, int dtype, int64_t idx, const V8& r) {
   if (dtype == ICF_F32) {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
@@ -510,9 +525,7 @@ __global__ void __launch_bounds__(VT) bn_bwd_reduce_v8(const void* dU, int ddt, 
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
   if (m.c0 < C) {
     const V8 mu = ldf8(mean + m.c0), is = ldf8(invstd + m.c0);
-    for (int64_t pix = m.pix0; pix < pixels; pix += m.pstride) {
-      V8 g = ld8(dU, ddt, pix * dpitch + m.c0);
-      const V8 yv = ld8(y, ydt, pix * ypitch + m.c0);
+    auto process = [&](int64_t pix, V8 g, const V8& yv) {
       if (mask) {
         const V8 mk = ldf8(mask + sample_of(pix, pps) * mpitch + m.c0);
 #pragma unroll
@@ -523,6 +536,27 @@ __global__ void __launch_bounds__(VT) bn_bwd_reduce_v8(const void* dU, int ddt, 
         acc[0][j] += g.v[j];
         acc[1][j] = fmaf(g.v[j], (yv.v[j] - mu.v[j]) * is.v[j], acc[1][j]);
       }
+    };
+    if (ddt == ICF_BF16 && ydt == ICF_BF16) {
+      for (int64_t pix = m.pix0; pix < pixels; pix += VU * m.pstride) {
+        uint4 gr[VU], yr[VU];
+#pragma unroll
+        for (int u = 0; u < VU; ++u) {
+          const int64_t pu = pix + u * m.pstride;
+          if (pu < pixels) {
+            gr[u] = ldraw8(dU, pu * dpitch + m.c0);
+            yr[u] = ldraw8(y, pu * ypitch + m.c0);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < VU; ++u) {
+          const int64_t pu = pix + u * m.pstride;
+          if (pu < pixels) process(pu, cvt8(gr[u]), cvt8(yr[u]));
+        }
+      }
+    } else {
+      for (int64_t pix = m.pix0; pix < pixels; pix += m.pstride)
+        process(pix, ld8(dU, ddt, pix * dpitch + m.c0), ld8(y, ydt, pix * ypitch + m.c0));
     }
   }
   float* dst[2] = {sums, sums + C};
@@ -570,10 +604,8 @@ __global__ void __launch_bounds__(VT) act_backward_v8(const icf_actbwd_args a) {
         }
       }
     }
-    for (int64_t pix = m.pix0; pix < a.pixels; pix += m.pstride) {
+    auto process = [&](int64_t pix, V8 g, const V8& yv) {
       const int64_t n = sample_of(pix, a.pixels_per_sample);
-      V8 g = ld8(a.dOut, a.d_dtype, pix * a.d_pitch + m.c0);
-      const V8 yv = ld8(a.y, a.y_dtype, pix * a.y_pitch + m.c0);
       if (bn) {
         if (a.bn_mask) {
           const V8 mk = ldf8(a.bn_mask + n * a.bn_mask_pitch + m.c0);
@@ -594,6 +626,28 @@ __global__ void __launch_bounds__(VT) act_backward_v8(const icf_actbwd_args a) {
         acc[0][j] += g.v[j];
       }
       st8(a.dPre, a.p_dtype, pix * a.p_pitch + m.c0, g);
+    };
+    if (a.d_dtype == ICF_BF16 && a.y_dtype == ICF_BF16) {
+      // raw 16-byte loads of VU pixels first, math afterwards: enough bytes in flight at 2-3 blocks per SM
+      for (int64_t pix = m.pix0; pix < a.pixels; pix += VU * m.pstride) {
+        uint4 gr[VU], yr[VU];
+#pragma unroll
+        for (int u = 0; u < VU; ++u) {
+          const int64_t pu = pix + u * m.pstride;
+          if (pu < a.pixels) {
+            gr[u] = ldraw8(a.dOut, pu * a.d_pitch + m.c0);
+            yr[u] = ldraw8(a.y, pu * a.y_pitch + m.c0);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < VU; ++u) {
+          const int64_t pu = pix + u * m.pstride;
+          if (pu < a.pixels) process(pu, cvt8(gr[u]), cvt8(yr[u]));
+        }
+      }
+    } else {
+      for (int64_t pix = m.pix0; pix < a.pixels; pix += m.pstride)
+        process(pix, ld8(a.dOut, a.d_dtype, pix * a.d_pitch + m.c0), ld8(a.y, a.y_dtype, pix * a.y_pitch + m.c0));
     }
   }
   if (a.dbias) {
