@@ -132,6 +132,9 @@ def run_reference(args):
 # our arm
 # -----------------------------------------------------------------------------------------------------------
 def run_ours(args):
+    if os.environ.get("ICF_WATCHDOG"):          # development aid: dump every thread's stack and exit if the run wedges
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["ICF_WATCHDOG"]), exit=True)
     import torch.distributed as dist
     from icf_b200 import ops, synth
     from icf_b200.arch import FAMILIES, forward_flops_per_image
@@ -235,6 +238,9 @@ def run_ours(args):
     # ---- per-kernel timing (eager replica of the step with CUDA events around every C-ABI launch) ----------
     roof = None
     kern = {}
+    if world > 1 and rank != 0:
+        tr.step(images, c)                             # the profiled replica runs collectives: every rank takes part
+        torch.cuda.synchronize()
     if rank == 0:
         ops.PROFILE = []
         tr.step(images, c)
@@ -303,9 +309,22 @@ def run_ours(args):
         except torch.cuda.OutOfMemoryError:
             cf = {"error": "out of memory"}
 
+    def shutdown():
+        """Tear NCCL down without risking a wedge: captured graphs that hold collectives are released first, and a
+        watchdog ends the process if destroy_process_group() still does not return."""
+        if world <= 1:
+            return
+        import gc
+        import threading
+        barrier()
+        tr.graph = None
+        gc.collect()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        dist.destroy_process_group()
+        os._exit(0)
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown()
         return
     cpu = None
     if not args.skip_cpu and world == 1:
@@ -334,8 +353,8 @@ def run_ours(args):
             "kernels_ms_per_step": kern,
             "counterfactual": cf}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    sys.stdout.flush()
+    shutdown()
 
 
 if __name__ == "__main__":

@@ -314,9 +314,18 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
         tmem_ld_wait();
         if (a < p.A) {
           float* o = p.dw + ((int64_t)a * p.taps + tap) * p.B + b0 + c0;
+          if (b0 + c0 + 16 <= p.B && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+            // four 16-byte vector reductions instead of sixteen scalar atomics (the split-K epilogue is L2-atomic bound)
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (b0 + c0 + j < p.B) atomicAdd(o + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 16; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(__uint_as_float(v[j])),
+                           "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (b0 + c0 + j < p.B) atomicAdd(o + j, __uint_as_float(v[j]));
+          }
         }
       }
     }
