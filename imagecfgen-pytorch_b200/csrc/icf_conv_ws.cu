@@ -79,7 +79,8 @@ struct WsParams {
   WsClass cls[WS_MAX_CLASSES];
 };
 
-// KD > 0: single 64-channel K chunk of KD 16-wide MMA steps (fully unrolled issue loop); KD == 0: generic
+// KD > 0: C spans KD 16-wide MMA steps (<= 8, i.e. up to two 64-channel chunks), issue loop fully unrolled;
+// KD == 0: generic
 #define WS_TIMED_WAIT(counter, bar, par)                    \
   do {                                                     \
     if (dbg_on) {                                          \
@@ -215,10 +216,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
           for (int t = t0; t < t1; ++t) {
             const uint32_t a_lo = a_lo0 + cl.taps[t].a_off16;
             const uint32_t b_lo = b_lo0 + (uint32_t)(t * p.kchunks) * WB16;
-            if (KD > 0) {
+            if (KD > 0) {              // KD 16-wide K steps, chunk boundary every 4 (fully unrolled)
 #pragma unroll
               for (int k = 0; k < KD; ++k) {
-                umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, accum, leader);
+                umma_bf16_lo(d_tmem, a_lo + (k >> 2) * kc16 + 2 * (k & 3), b_lo + (k >> 2) * WB16 + 2 * (k & 3), desc_hi,
+                             idesc, accum, leader);
                 accum = 1u;
               }
             } else {
@@ -591,14 +593,18 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   size_t smem = (size_t)q.slab_bytes + (size_t)q.n_slots * q.slot_bytes + (size_t)stage_bytes + 1024 + 1024;
   if (smem < 120 * 1024) smem = 120 * 1024;
   int r;
-  const int kd = q.kchunks == 1 ? q.kdepth_last : 0;
+  const int kd = q.kchunks <= 2 ? 4 * (q.kchunks - 1) + q.kdepth_last : 0;
 #define ICF_WS_CASE(TN)                                                        \
   switch (kd) {                                                                \
-    case 1: r = launch_ws<TN, 1>(ma, mb, mo, q, grid, smem, st); break;            \
-    case 2: r = launch_ws<TN, 2>(ma, mb, mo, q, grid, smem, st); break;            \
-    case 3: r = launch_ws<TN, 3>(ma, mb, mo, q, grid, smem, st); break;            \
-    case 4: r = launch_ws<TN, 4>(ma, mb, mo, q, grid, smem, st); break;            \
-    default: r = launch_ws<TN, 0>(ma, mb, mo, q, grid, smem, st); break;           \
+    case 1: r = launch_ws<TN, 1>(ma, mb, mo, q, grid, smem, st); break;        \
+    case 2: r = launch_ws<TN, 2>(ma, mb, mo, q, grid, smem, st); break;        \
+    case 3: r = launch_ws<TN, 3>(ma, mb, mo, q, grid, smem, st); break;        \
+    case 4: r = launch_ws<TN, 4>(ma, mb, mo, q, grid, smem, st); break;        \
+    case 5: r = launch_ws<TN, 5>(ma, mb, mo, q, grid, smem, st); break;        \
+    case 6: r = launch_ws<TN, 6>(ma, mb, mo, q, grid, smem, st); break;        \
+    case 7: r = launch_ws<TN, 7>(ma, mb, mo, q, grid, smem, st); break;        \
+    case 8: r = launch_ws<TN, 8>(ma, mb, mo, q, grid, smem, st); break;        \
+    default: r = launch_ws<TN, 0>(ma, mb, mo, q, grid, smem, st); break;       \
   }
   switch (tile_n) {
     case 16: ICF_WS_CASE(16) break;
