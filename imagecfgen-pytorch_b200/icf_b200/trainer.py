@@ -78,6 +78,7 @@ class BiGANTrainer:
         self.lr, self.betas, self.eps = lr, betas, eps
         self.overlap = overlap_allreduce and self.world > 1
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.overlap else None
+        self.mask_stream = torch.cuda.Stream(device=self.device)      # Dropout2d masks are drawn off the critical path
         self.graph = None
         self.static = None
         for ex in (self.exE, self.exG, self.exD):
@@ -122,8 +123,22 @@ class BiGANTrainer:
         z = z.contiguous().float()
         xp, xc = x.data_ptr(), ops.code_of(x)
         zp = z.data_ptr()
+        mask_ev = None
         if masks6 is None:
             masks6 = [None] * 6
+            if exD.sites:
+                # Draw the Dropout2d masks of this step's D forwards up front on a side stream (~120 tiny RNG kernels that
+                # would otherwise sit between the convolutions), in the order the reference consumes the generator:
+                # A-valid, A-fake, B, C, D-fake, D-valid (mnist.py:224-248).
+                cur = torch.cuda.current_stream()
+                self.mask_stream.wait_stream(cur)
+                with torch.cuda.stream(self.mask_stream):
+                    for i in (range(6) if phase_a else range(2, 6)):
+                        masks6[i] = draw_masks(fam, N, self.device)
+                        for m in masks6[i]:
+                            m.record_stream(cur)
+                    mask_ev = torch.cuda.Event()
+                    mask_ev.record()
         if out is None:
             out = torch.zeros(8, dtype=torch.float32, device=self.device)
         dl = torch.empty((N, 1), dtype=torch.float32, device=self.device)
@@ -135,6 +150,9 @@ class BiGANTrainer:
                 ops.fill_f32(self.gEG.grad.data_ptr(), 0.0, self.gEG.n)
                 zE, stE = exE.encoder_forward(N, xp, xc, 1, c, save=True)
                 xG, stG = exG.generator_forward(N, zp, F32, fam.latent, c, save=True)
+                if mask_ev is not None:
+                    torch.cuda.current_stream().wait_event(mask_ev)
+                    mask_ev = None
                 l1, sD1 = exD.discriminator_forward(N, xp, xc, 1, zE.ptr, zE.code, zE.pitch, c, masks=masks6[0])
                 l2, sD2 = exD.discriminator_forward(N, xG.ptr, xG.code, xG.pitch, zp, F32, fam.latent, c,
                                                     masks=masks6[1])
@@ -157,6 +175,8 @@ class BiGANTrainer:
             # ---- Phase B: discriminator on real pairs (mnist.py:232-236) -------------------------------
             ops.fill_f32(self.gD.grad.data_ptr(), 0.0, self.gD.n)
             zE, _ = exE.encoder_forward(N, xp, xc, 1, c, save=False)
+            if mask_ev is not None:
+                torch.cuda.current_stream().wait_event(mask_ev)
             l, sD = exD.discriminator_forward(N, xp, xc, 1, zE.ptr, zE.code, zE.pitch, c, masks=masks6[2])
             ops.bce_logits(l.ptr, F32, 1, N, 1.0, 1.0, ops.ptr(out, 1), dl.data_ptr(), F32, 1)
             exD.discriminator_backward(sD, Act(dl, 1), self.gradsD)
