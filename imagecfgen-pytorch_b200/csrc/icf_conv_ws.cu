@@ -74,6 +74,7 @@ struct WsParams {
   const float* bias;
   const float* mask;
   void* dst;
+  float* stats;                // [2][K] BatchNorm statistics of the stored values (+=), fused into the TMA-store epilogue
   int tma_store;               // 1: epilogue stages bf16 rows in shared memory and leaves through a TMA tensor store
   unsigned long long* dbg;     // optional per-role cycle counters of CTA 0 (env ICF_WS_DEBUG), else NULL
   WsClass cls[WS_MAX_CLASSES];
@@ -255,6 +256,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     for (int j = (int)threadIdx.x - 32 * (1 + WS_ISSUERS); j < TILE_N; j += 128) sbias[j] = (p.bias && k0 + j < p.K) ? __ldg(p.bias + k0 + j) : 0.f;
     asm volatile("bar.sync 1, 128;" ::: "memory");
     const int esize = p.out_f32 ? 4 : 2;
+    // fused BatchNorm statistics: thread -> one 8-channel chunk (et % CH) of the staged tile and every (128/CH)-th row
+    constexpr int CH = TILE_N / 8;
+    const int et = (int)threadIdx.x - 32 * (1 + WS_ISSUERS);
+    const int st_ch = et % CH, st_r0 = et / CH;
+    float st_sum[8], st_sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) st_sum[j] = st_sq[j] = 0.f;
     int g = 0;
     for (int col = r0; col < ncols; col += rstep) {
       const int jt = col % cl.tiles_x, nt = col / cl.tiles_x;
@@ -313,6 +321,28 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
             tma_store_4d(&map_o, smem_u32(stage) + buf, k0, n0, ox, cl.py + i * p.ostep);
             bulk_commit();
           }
+          if (p.stats) {
+            // column sums of the staged (bf16-rounded, as stored) tile, 16 bytes per load; rows beyond the batch /
+            // row end are skipped
+            const bool full = n0 + p.NG <= p.N && jt * p.XG + p.XG <= cl.Qj;
+            const uint8_t* tile = stage + buf;
+#pragma unroll
+            for (int rr = 0; rr < CH; ++rr) {
+              const int row = st_r0 + rr * (128 / CH);
+              if (!full && !(n0 + (row & (p.NG - 1)) < p.N && jt * p.XG + (row >> p.ng_shift) < cl.Qj)) continue;
+              const uint32_t rsw = TILE_N == 64 ? (uint32_t)(row & 7) : (TILE_N == 32 ? (uint32_t)((row >> 1) & 3) : (uint32_t)((row >> 2) & 1));
+              const uint4 w4 = *reinterpret_cast<const uint4*>(tile + (uint32_t)row * ROW_B + (((uint32_t)st_ch ^ rsw) << 4));
+              const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xFFFF0000u);
+                st_sum[2 * j] += lo;
+                st_sq[2 * j] = fmaf(lo, lo, st_sq[2 * j]);
+                st_sum[2 * j + 1] += hi;
+                st_sq[2 * j + 1] = fmaf(hi, hi, st_sq[2 * j + 1]);
+              }
+            }
+          }
         }
         continue;
       }
@@ -358,6 +388,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
       }
     }
     if (p.tma_store && (int)threadIdx.x == 32 * (1 + WS_ISSUERS)) bulk_wait_all();
+    if (p.tma_store && p.stats) {
+      // lanes that share a chunk (same et % CH) first combine through shuffles, then one atomic per channel and warp
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int o = CH; o < 32; o <<= 1) {
+          st_sum[j] += __shfl_xor_sync(0xffffffffu, st_sum[j], o);
+          st_sq[j] += __shfl_xor_sync(0xffffffffu, st_sq[j], o);
+        }
+      }
+      if (lane < CH) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = k0 + st_ch * 8 + j;
+          if (k < p.K) {
+            atomicAdd(p.stats + k, st_sum[j]);
+            atomicAdd(p.stats + p.K + k, st_sq[j]);
+          }
+        }
+      }
+    }
     if (dbg_on && threadIdx.x == 32 * (1 + WS_ISSUERS)) { p.dbg[5] = clock64() - t_begin; p.dbg[6] = w0; p.dbg[7] = w1; }
   }
   tc_fence_before();
@@ -563,6 +614,7 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
     static const bool off = []() { const char* e = getenv("ICF_WS_NO_TMA_STORE"); return e && e[0] && e[0] != '0'; }();
     if (off) q.tma_store = 0;
   }
+  q.stats = (q.tma_store && a->stats) ? a->stats : nullptr;
   if (q.tma_store) {
     int kp = (a->K + 7) & ~7;                       // ragged K: the pitch padding is written as zeros
     if (kp > a->out_pitch) kp = a->K;
@@ -613,6 +665,7 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   }
 #undef ICF_WS_CASE
   if (r) return r;
+  const bool stats_fused = q.stats != nullptr;
   if (q.dbg) {
     unsigned long long h[8];
     cudaStreamSynchronize(st);
@@ -623,7 +676,7 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
             a->K, a->C, a->R, a->stride, a->form, tile_n, q.XG, q.NG, q.n_slots, q.slot_bytes, q.slab_bytes, grid, h[0], h[1],
             h[2], h[3], h[4], h[5], h[6], h[7]);
   }
-  if (a->stats) {
+  if (a->stats && !stats_fused) {
     if (a->out_f32) { icf::set_error("row-streaming conv: BatchNorm statistics need a bf16 destination"); return 1; }
     return icf_launch_col_stats(a->dst, ICF_BF16, a->out_pitch, (int64_t)a->N * a->P * a->Q, a->K, a->stats, st);
   }
