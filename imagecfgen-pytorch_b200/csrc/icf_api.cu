@@ -8,6 +8,7 @@
 int icf_simt_conv_forward(const icf_conv_args* a, cudaStream_t st);
 int icf_simt_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st);
 int icf_b1_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st);
+int icf_px8_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st);
 
 namespace icf {
 
@@ -101,6 +102,8 @@ int icf_conv_wgrad(const icf_wgrad_args* a, void* stream) {
   cudaStream_t st = icf::as_stream(stream);
   if (a->dtype == ICF_BF16 && icf_tc_enabled()) {
     int r = icf_b1_conv_wgrad(a, st);        // single-channel gradient operand: HBM-bound streaming reduction
+    if (r >= 0) return r;
+    r = icf_px8_conv_wgrad(a, st);           // unit-stride first layer on the 8-channel-pitch feature tensor
     if (r >= 0) return r;
     r = icf_tc_conv_wgrad(a, st);
     if (r >= 0) return r;

@@ -133,6 +133,22 @@ __device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uin
       "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
+// as umma_bf16_lo, with independent high words (operands of different layouts / strides)
+__device__ __forceinline__ void umma_bf16_lo2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "setp.ne.b32 q, %7, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_if(uint32_t bar, uint32_t leader) {
   asm volatile(
       "{\n"

@@ -142,6 +142,30 @@ def test_conv_wgrad(case, code):
     assert err < (1e-5 if code == 0 else 1e-4), err      # inputs pre-rounded to bf16, fp32 accumulation
 
 
+@pytest.mark.parametrize("case", [(6, 5, 28, 32, 5), (150, 5, 28, 32, 5), (3, 7, 20, 64, 3), (2, 2, 33, 16, 4)],
+                         ids=lambda c: str(c))
+def test_conv_wgrad_first_layer_folded(case):
+    """Unit-stride first-layer weight gradient on the 8-channel-pitch feature tensor in the folded ("win") packing
+    dw[k][r][s*8 + c] (the form engine.LayerExec uses for D.dx.1): overlapping-window descriptor kernel."""
+    ops = ops_mod()
+    N, C, H, K, k = case
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, C, H, H, generator=g).bfloat16().float()
+    P = H - k + 1
+    dy = torch.randn(N, K, P, P, generator=g).bfloat16().float()
+    w = torch.zeros(K, C, k, k, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), w, None, 1, 0).backward(dy.double())
+    kp = (K + 7) // 8 * 8
+    xt, dyt = nhwc(x, 8, torch.bfloat16), nhwc(dy, kp, torch.bfloat16)
+    xt = torch.cat([xt, torch.zeros(H, 8, dtype=torch.bfloat16, device=DEV)])      # slack rows the folded reads run into
+    dwp = torch.zeros(K * k * k * 8, dtype=torch.float32, device=DEV)
+    ops.conv_wgrad(1, N, P, P, K, kp, H, H, k * 8, 8, k, 1, 1, 0, dyt.data_ptr(), xt.data_ptr(), dwp.data_ptr(), win=k)
+    torch.cuda.synchronize()
+    got = dwp.view(K, k, k, 8)[..., :C].permute(0, 3, 1, 2).cpu().double()        # [K][r][s][c] -> [K][c][r][s]
+    err = rel_err(got, w.grad)
+    assert err < 1e-4, err
+
+
 def test_argmax_first_max_wins():
     ops = ops_mod()
     x = torch.tensor([[0, 0, 0], [0, 1, 1], [2, 2, 1], [0.5, 0.2, 0.9]], device=DEV)
