@@ -24,6 +24,7 @@ constexpr int PX_SLOTS = 3;
 
 struct PxParams {
   int N, P, Q, A, R, B;                  // B = win*8 valid columns
+  int PB, pblocks;                       // rows of dY per work item, work items per image
   int ksteps;                            // 16-pixel reduction steps per image row
   int QP, WP;                            // q extent of the dY tile, x extent of the X tile (elements of 16 B)
   uint32_t dy_bytes, x_bytes, slot_bytes;
@@ -86,12 +87,14 @@ __global__ void __launch_bounds__(PX_THREADS, 1) wgrad_px8_kernel(const __grid_c
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
+      const int items = p.N * p.pblocks;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int n = it / p.pblocks, p0 = (it - n * p.pblocks) * p.PB;
         mbar_wait(empty_bar(s), ph ^ 1);
         mbar_expect_tx(full_bar(s), p.dy_bytes + p.x_bytes);
         const uint32_t base = smem_base + (uint32_t)s * p.slot_bytes;
-        tma_load_5d(base, &map_dy, full_bar(s), 0, 0, 0, 0, n);
-        tma_load_4d(base + p.dy_bytes, &map_x, full_bar(s), 0, 0, 0, n);
+        tma_load_5d(base, &map_dy, full_bar(s), 0, 0, 0, p0, n);        // rows beyond P arrive as zeros
+        tma_load_4d(base + p.dy_bytes, &map_x, full_bar(s), 0, 0, p0, n);
         if (++s == PX_SLOTS) { s = 0; ph ^= 1; }
       }
     }
@@ -108,12 +111,15 @@ __global__ void __launch_bounds__(PX_THREADS, 1) wgrad_px8_kernel(const __grid_c
     int s = 0;
     uint32_t ph = 0;
     uint32_t first = 0;                                                         // accumulate flag (0 only for the very first step)
-    for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
+    const int items = p.N * p.pblocks;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
       const uint32_t a_img = ((smem_base + (uint32_t)s * p.slot_bytes) >> 4) & 0x3FFFu;
       const uint32_t b_img = ((smem_base + (uint32_t)s * p.slot_bytes + p.dy_bytes) >> 4) & 0x3FFFu;
-      for (int pr = 0; pr < p.P; ++pr) {
+      const int p0 = (it % p.pblocks) * p.PB;
+      const int rows = p.P - p0 < p.PB ? p.P - p0 : p.PB;
+      for (int pr = 0; pr < rows; ++pr) {
         for (int ks = 0; ks < p.ksteps; ++ks) {
           const uint32_t a_lo = a_lo0 | (a_img + (uint32_t)pr * row_a16 + (uint32_t)ks * 16u);
           for (int r = wi; r < p.R; r += PX_ISSUERS) {
@@ -133,7 +139,7 @@ __global__ void __launch_bounds__(PX_THREADS, 1) wgrad_px8_kernel(const __grid_c
     const int a = q4 * 32 + lane;
     mbar_wait(done_bar, 0);
     tc_fence_after();
-    if (blockIdx.x < p.N) {
+    if ((int)blockIdx.x < p.N * p.pblocks) {
       for (int r = 0; r < p.R; ++r)
         for (int c0 = 0; c0 < (int)p.n_cols; c0 += 16) {
           uint32_t v[16];
@@ -185,9 +191,15 @@ int icf_px8_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
   p.QP = 16 * p.ksteps;
   p.n_cols = (uint32_t)((a->B + 15) & ~15);
   p.WP = p.QP + (int)p.n_cols / 8;                 // widest pixel a column group of the last reduction row touches
-  if (p.P > 256 || a->H > 256 || p.QP > 256 || p.WP > 256) return -1;
-  p.dy_bytes = (uint32_t)(a->P * (a->A / 8) * p.QP) * 16u;
-  p.x_bytes = (uint32_t)(a->H * p.WP) * 16u;
+  if (p.QP > 256 || p.WP > 256) return -1;
+  const int row_bytes = (a->A / 8) * p.QP * 16;
+  p.PB = (56 * 1024) / row_bytes;                  // rows of dY per work item: keep a ring slot near 64 KB
+  if (p.PB < 1) return -1;
+  if (p.PB > a->P) p.PB = a->P;
+  if (p.PB + a->R - 1 > 256) p.PB = 256 - (a->R - 1);
+  p.pblocks = icf::cdiv(a->P, p.PB);
+  p.dy_bytes = (uint32_t)(p.PB * row_bytes);
+  p.x_bytes = (uint32_t)((p.PB + a->R - 1) * p.WP) * 16u;
   p.slot_bytes = (p.dy_bytes + p.x_bytes + 1023u) & ~1023u;
   const uint32_t cols = (uint32_t)a->R * p.n_cols;
   if (cols > 512) return -1;
@@ -202,13 +214,13 @@ int icf_px8_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
     cuuint64_t dims[5] = {8, (cuuint64_t)a->Q, (cuuint64_t)(a->A / 8), (cuuint64_t)a->P, (cuuint64_t)a->N};
     cuuint64_t str[4] = {(cuuint64_t)a->a_pitch * 2, 16, (cuuint64_t)a->Q * a->a_pitch * 2,
                          (cuuint64_t)a->P * a->Q * a->a_pitch * 2};
-    cuuint32_t box[5] = {8, (cuuint32_t)p.QP, (cuuint32_t)(a->A / 8), (cuuint32_t)a->P, 1};
+    cuuint32_t box[5] = {8, (cuuint32_t)p.QP, (cuuint32_t)(a->A / 8), (cuuint32_t)p.PB, 1};
     if (int r = encode_plain(&mdy, a->small_t, 5, dims, str, box)) return r;
   }
   {
     cuuint64_t dims[4] = {8, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N};
     cuuint64_t str[3] = {16, (cuuint64_t)a->W * 16, (cuuint64_t)a->H * a->W * 16};
-    cuuint32_t box[4] = {8, (cuuint32_t)p.WP, (cuuint32_t)a->H, 1};
+    cuuint32_t box[4] = {8, (cuuint32_t)p.WP, (cuuint32_t)(p.PB + a->R - 1), 1};
     if (int r = encode_plain(&mx, a->big_t, 4, dims, str, box)) return r;
   }
   static size_t configured = 0;
@@ -219,7 +231,8 @@ int icf_px8_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
   }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = a->N < sms ? a->N : sms;
+  const int64_t items = (int64_t)a->N * p.pblocks;
+  const int grid = items < sms ? (int)items : sms;
   wgrad_px8_kernel<<<grid, PX_THREADS, smem, st>>>(mdy, mx, p);
   return icf::check_launch("wgrad_px8");
 }

@@ -130,6 +130,13 @@ class LayerExec:
             self.perm_fold = ops.make_perm4(K_, self.R, self.S, C_, C_ * T, self.S, 1, T, 8, self.fold_pitch)
             self.perm_fold_g = ops.make_perm4(K_, self.R, self.S, C_, C_ * T, self.S, 1, T, 8, self.S * 8)
             self.wgrad_elems = K_ * self.R * self.S * 8
+        # single-output-channel ConvTranspose2d tail (stride 1, no padding, bf16): its weight gradient is the
+        # overlapping-window form dw[c][r][s*8 + 0] over the 8-channel-pitch gradient tensor (icf_wgrad_px8.cu)
+        self.px8 = (spec.kind == "convT" and code == BF16 and self.Kout == 1 and self.stride == 1 and self.pad == 0
+                    and self.Cin % 8 == 0 and self.Cin <= 128 and self.S >= 2)
+        if self.px8:
+            self.perm_px8_g = ops.make_perm4(C_, self.R, self.S, 1, self.R * self.S, self.S, 1, self.R * self.S, 8, self.S * 8)
+            self.wgrad_elems = max(self.wgrad_elems, C_ * self.R * self.S * 8)
         self.alg_flops_img = 2.0 * self.Cin * self.Kout * ops.valid_taps(self.form, hin, self.P, self.R, self.stride, self.pad) \
             * ops.valid_taps(self.form, win, self.Q, self.S, self.stride, self.pad)
 
@@ -187,6 +194,12 @@ class LayerExec:
                            self.Win + 2 * self.pad, self.fold * x.pitch, x.pitch, self.R, 1, self.stride, 0, dpre.ptr,
                            x.ptr, scratch.data_ptr(), win=self.fold, alg_flops=self.alg_flops_img * N)
             ops.unpack4(scratch.data_ptr(), gw.data_ptr(), self.perm_fold_g)
+            return
+        if self.px8 and dpre.pitch == 8:
+            ops.conv_wgrad(self.code, N, self.Hin, self.Win, self.Cin, x.pitch, self.P, self.Q, self.S * 8, 8,
+                           self.R, 1, 1, 0, x.ptr, dpre.ptr, scratch.data_ptr(), win=self.S,
+                           alg_flops=self.alg_flops_img * N)
+            ops.unpack4(scratch.data_ptr(), gw.data_ptr(), self.perm_px8_g)
             return
         lin = self.spec.kind == "linear"
         dp_pitch = dpre.pitch * self.Hout * self.Wout if lin else dpre.pitch
