@@ -756,6 +756,34 @@ __global__ void pack_kernel(const float* __restrict__ src, void* dst, int ddt, c
   }
 }
 
+__global__ void pack_multi_kernel(const icf_pack_job* __restrict__ jobs) {
+  const icf_pack_job jb = jobs[blockIdx.y];
+  if (jb.kind == 0) {
+    const icf_perm p = jb.p;
+    const int64_t total = p.d0_pad * p.d1 * p.d2_pad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t i2 = i % p.d2_pad;
+      const int64_t t = i / p.d2_pad;
+      const int64_t i1 = t % p.d1, i0 = t / p.d1;
+      float v = 0.f;
+      if (i2 < p.d2 && i0 < p.d0) v = jb.src[i0 * p.s0 + i1 * p.s1 + i2 * p.s2];
+      icf::st_any(jb.dst, jb.dst_dtype, i, v);
+    }
+  } else {
+    const icf_perm4 p = jb.p4;
+    const int64_t total = p.d0 * p.d1 * p.row_pitch;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t col = i % p.row_pitch;
+      const int64_t t = i / p.row_pitch;
+      const int64_t i1 = t % p.d1, i0 = t / p.d1;
+      const int64_t i2 = col / p.d3_pad, i3 = col % p.d3_pad;
+      float v = 0.f;
+      if (i2 < p.d2 && i3 < p.d3) v = jb.src[i0 * p.s0 + i1 * p.s1 + i2 * p.s2 + i3 * p.s3];
+      icf::st_any(jb.dst, jb.dst_dtype, i, v);
+    }
+  }
+}
+
 __global__ void unpack_kernel(const float* __restrict__ src, float* dst, const icf_perm p, int atomic_add) {
   const int64_t total = p.d0 * p.d1 * p.d2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -999,6 +1027,15 @@ int icf_pack(const float* src, void* dst, int32_t dst_dtype, const icf_perm* p, 
   if (total == 0) return 0;
   pack_kernel<<<ew_grid(total), EW_THREADS, 0, icf::as_stream(stream)>>>(src, dst, dst_dtype, *p);
   return icf::check_launch("pack");
+}
+
+int icf_pack_multi(const icf_pack_job* jobs, int32_t n_jobs, int64_t max_elems, void* stream) {
+  ICF_REQUIRE(jobs && n_jobs >= 0 && max_elems >= 0, "icf_pack_multi: bad arguments");
+  if (n_jobs == 0 || max_elems == 0) return 0;
+  int64_t bx = (max_elems + EW_THREADS - 1) / EW_THREADS;
+  if (bx > 64) bx = 64;
+  pack_multi_kernel<<<dim3((unsigned)bx, (unsigned)n_jobs), EW_THREADS, 0, icf::as_stream(stream)>>>(jobs);
+  return icf::check_launch("pack_multi");
 }
 
 int icf_unpack(const float* src_packed, float* dst, const icf_perm* p, int32_t atomic_add, void* stream) {

@@ -141,18 +141,26 @@ class LayerExec:
             * ops.valid_taps(self.form, win, self.Q, self.S, self.stride, self.pad)
 
     # ---- operands -------------------------------------------------------------------------------
-    def repack(self, weight: torch.Tensor, bias: torch.Tensor):
-        ops.pack(weight.data_ptr(), self.w_fwd.data_ptr(), self.code, self.perm_f)
-        ops.pack(weight.data_ptr(), self.w_bwd.data_ptr(), self.code, self.perm_b)
+    def pack_jobs(self, weight: torch.Tensor, bias: torch.Tensor):
+        """[(src ptr, dst ptr, dst dtype, perm)] that refresh this layer's operand copies from its parameters."""
+        wp, bp = weight.data_ptr(), bias.data_ptr()
+        jobs = [(wp, self.w_fwd.data_ptr(), self.code, self.perm_f), (wp, self.w_bwd.data_ptr(), self.code, self.perm_b)]
         if self.fold:
-            ops.pack4(weight.data_ptr(), self.w_fold.data_ptr(), self.code, self.perm_fold)
+            jobs.append((wp, self.w_fold.data_ptr(), self.code, self.perm_fold))
         if self.perm_bias is None:
-            ops.cast(bias.data_ptr(), F32, self.bias.data_ptr(), F32, self.Kout)
+            jobs.append((bp, self.bias.data_ptr(), F32, ops.make_perm(1, 1, self.Kout, 0, 0, 1)))
         else:
-            ops.pack(bias.data_ptr(), self.bias.data_ptr(), F32, self.perm_bias)
+            jobs.append((bp, self.bias.data_ptr(), F32, self.perm_bias))
         if self.gemm_fwd:
-            ops.pack(weight.data_ptr(), self.w_gemm.data_ptr(), self.code, self.perm_gemm)
-            ops.pack(bias.data_ptr(), self.bias_gemm.data_ptr(), F32, self.perm_bias_gemm)
+            jobs.append((wp, self.w_gemm.data_ptr(), self.code, self.perm_gemm))
+            jobs.append((bp, self.bias_gemm.data_ptr(), F32, self.perm_bias_gemm))
+        return jobs
+
+    def repack(self, weight: torch.Tensor, bias: torch.Tensor):
+        """Stand-alone refresh of this layer (tools / tests); NetExec.repack batches all layers into one launch."""
+        from .lib import Perm4
+        for src, dst, dt, perm in self.pack_jobs(weight, bias):
+            (ops.pack4 if isinstance(perm, Perm4) else ops.pack)(src, dst, dt, perm)
 
     # ---- launches -------------------------------------------------------------------------------
     def forward(self, N, x: Act, y: Act, mask=None, mask_pitch=0, stats=None, out_f32=False):
@@ -272,6 +280,8 @@ class NetExec:
                            "Dxz": Tower(fam.Dxz, 1, 1, code, device)}
             self.sites = mask_sites(fam)
         self._versions = None
+        self._pack_table = None
+        self._pack_ptrs = None
         self._scratch = None
         self.emb_key = 2 if role != "G" else 3      # index into fam.cat_attrs tuples
 
@@ -292,8 +302,13 @@ class NetExec:
         vers = tuple((k, v._version, v.data_ptr()) for k, v in ts.items() if k.endswith(("weight", "bias")))
         if not force and vers == self._versions:
             return
-        for le in self.all_layers():
-            le.repack(ts[le.spec.key + ".weight"], ts[le.spec.key + ".bias"])
+        ptrs = tuple(v.data_ptr() for k, v in ts.items() if k.endswith(("weight", "bias")))
+        if self._pack_table is None or self._pack_ptrs != ptrs:        # one device-side job table per parameter placement
+            jobs = []
+            for le in self.all_layers():
+                jobs += le.pack_jobs(ts[le.spec.key + ".weight"], ts[le.spec.key + ".bias"])
+            self._pack_table, self._pack_ptrs = ops.PackTable(jobs, self.device), ptrs
+        self._pack_table.run()                                         # every operand copy of the network, one launch
         self._versions = vers
 
     def scratch(self):

@@ -47,6 +47,10 @@ class Perm4(C.Structure):
                 ("s3", _i64), ("d3_pad", _i64), ("row_pitch", _i64)]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("src", _vp), ("dst", _vp), ("dst_dtype", _i32), ("kind", _i32), ("p", Perm), ("p4", Perm4)]
+
+
 class ImgFeatArgs(C.Structure):
     _fields_ = [("dtype", _i32), ("N", _i32), ("H", _i32), ("W", _i32), ("feat_pitch", _i32),
                 ("x_dtype", _i32), ("x_pitch", _i32), ("n_emb", _i32), ("n_cont", _i32),
@@ -86,6 +90,7 @@ _SIGS = {
     "icf_conv_forward": (_i32, [C.POINTER(ConvArgs), _vp]),
     "icf_conv_wgrad": (_i32, [C.POINTER(WgradArgs), _vp]),
     "icf_pack": (_i32, [_vp, _vp, _i32, C.POINTER(Perm), _vp]),
+    "icf_pack_multi": (_i32, [_vp, _i32, _i64, _vp]),
     "icf_unpack": (_i32, [_vp, _vp, C.POINTER(Perm), _i32, _vp]),
     "icf_pack4": (_i32, [_vp, _vp, _i32, C.POINTER(Perm4), _vp]),
     "icf_unpack4": (_i32, [_vp, _vp, C.POINTER(Perm4), _vp]),

@@ -123,6 +123,19 @@ typedef struct icf_perm4 {
 int icf_pack4(const float* src, void* dst, int32_t dst_dtype, const icf_perm4* p, void* stream);
 int icf_unpack4(const float* src_packed, float* dst, const icf_perm4* p, void* stream);
 
+/* All re-packing jobs of a network in ONE launch (after an optimiser step every layer's operand copies are stale:
+ * ~30 tiny launches per network otherwise).  `jobs` is an array in DEVICE memory, uploaded once by the caller;
+ * kind 0 = icf_perm job (p), kind 1 = icf_perm4 job (p4); max_elems = largest padded element count of any job. */
+typedef struct icf_pack_job {
+  const float* src;
+  void* dst;
+  int32_t dst_dtype;
+  int32_t kind;
+  icf_perm p;
+  icf_perm4 p4;
+} icf_pack_job;
+int icf_pack_multi(const icf_pack_job* jobs, int32_t n_jobs, int64_t max_elems, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Attribute / latent feature assembly (mnist.py:47-55,77-85; audio_mnist.py:204-210,250-256).
  * ------------------------------------------------------------------------------------------------ */
