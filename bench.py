@@ -284,6 +284,26 @@ def run_ours(args):
                     "launches": conv["n"], "avg_launch_ms": conv["ms"] / conv["n"], "share_of_step": conv["ms"] / total,
                     "peak_source": f"bf16_tflops_sustained, {pk['src']}",
                     "hbm_frac_same_launches": conv["bytes"] / (conv["ms"] * 1e-3) / 1e9 / pk["hbm"]}
+            # the single most expensive conv layer of the step against ITS roofline (max of tensor / HBM time); `traffic` =
+            # DRAM bytes per launch of that layer from the committed `ncu --set full` capture when one exists
+            convs = [(det, d) for det, d in layers.items() if det.startswith(("gather", "transp", "wgrad"))]
+            if convs:
+                det, d = max(convs, key=lambda kv: kv[1]["ms"])
+                sec1 = d["ms"] * 1e-3 / d["n"]
+                fl1, by1 = d["flops"] / d["n"], d["bytes"] / d["n"]
+                hbm_bound = by1 / (pk["hbm"] * 1e9) > fl1 / (pk["tf_sust"] * 1e12)
+                traffic = None
+                try:
+                    with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as tf:
+                        traffic = json.load(tf).get(det)
+                except Exception:
+                    traffic = None
+                roof["dominant_layer"] = {
+                    "layer": det, "launches": d["n"], "avg_launch_ms": d["ms"] / d["n"], "bound": "hbm" if hbm_bound else "tensor",
+                    "achieved": by1 / sec1 / 1e9 if hbm_bound else fl1 / sec1 / 1e12,
+                    "peak": pk["hbm"] if hbm_bound else pk["tf_sust"], "unit": "GB/s" if hbm_bound else "TFLOP/s",
+                    "frac": (by1 / sec1 / 1e9 / pk["hbm"]) if hbm_bound else (fl1 / sec1 / 1e12 / pk["tf_sust"]),
+                    "algorithmic_bytes_per_launch": by1, "traffic": traffic}
         kern = {k: {"ms": round(v["ms"], 4), "n": v["n"]} for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}
 
     # ---- counterfactual pipeline (BASELINE.json configs[2]) --------------------------------------------------

@@ -137,6 +137,8 @@ class LayerExec:
         if self.px8:
             self.perm_px8_g = ops.make_perm4(C_, self.R, self.S, 1, self.R * self.S, self.S, 1, self.R * self.S, 8, self.S * 8)
             self.wgrad_elems = max(self.wgrad_elems, C_ * self.R * self.S * 8)
+        # algorithmic bytes per image (each tensor touched once, real channels — not the folded / padded operand widths)
+        self.alg_bytes_img = 2.0 * (hin * win * self.Cin + self.Hout * self.Wout * self.Cout)
         self.alg_flops_img = 2.0 * self.Cin * self.Kout * ops.valid_taps(self.form, hin, self.P, self.R, self.stride, self.pad) \
             * ops.valid_taps(self.form, win, self.Q, self.S, self.stride, self.pad)
 
@@ -170,7 +172,8 @@ class LayerExec:
                              self.fold * x.pitch, x.pitch, self.P, self.Q, self.Kout, y.pitch, self.R, 1, self.stride, 0,
                              x.ptr, self.w_fold.data_ptr(), self.Kout, self.fold_pitch, y.ptr, bias=self.bias.data_ptr(),
                              act=sp.act, slope=sp.slope, out_f32=out_f32, mask=mask, mask_pitch=mask_pitch, stats=stats,
-                             win=self.fold, alg_flops=self.alg_flops_img * N)
+                             win=self.fold, alg_flops=self.alg_flops_img * N,
+                             alg_bytes=self.alg_bytes_img * N + 2.0 * self.wgrad_elems)
             return
         if self.gemm_fwd and mask is None and stats is None and y.pitch == self.Kout and y.off == 0:
             ops.conv_forward(self.code, ops.GATHER, N, 1, 1, self.Cin, x.pitch, 1, 1, self.taps * self.Kout,
@@ -200,13 +203,14 @@ class LayerExec:
         if self.fold:
             ops.conv_wgrad(self.code, N, self.P, self.Q, self.Kout, dpre.pitch, self.Hin + 2 * self.pad,
                            self.Win + 2 * self.pad, self.fold * x.pitch, x.pitch, self.R, 1, self.stride, 0, dpre.ptr,
-                           x.ptr, scratch.data_ptr(), win=self.fold, alg_flops=self.alg_flops_img * N)
+                           x.ptr, scratch.data_ptr(), win=self.fold, alg_flops=self.alg_flops_img * N,
+                           alg_bytes=self.alg_bytes_img * N + 4.0 * self.wgrad_elems)
             ops.unpack4(scratch.data_ptr(), gw.data_ptr(), self.perm_fold_g)
             return
         if self.px8 and dpre.pitch == 8:
             ops.conv_wgrad(self.code, N, self.Hin, self.Win, self.Cin, x.pitch, self.P, self.Q, self.S * 8, 8,
                            self.R, 1, 1, 0, x.ptr, dpre.ptr, scratch.data_ptr(), win=self.S,
-                           alg_flops=self.alg_flops_img * N)
+                           alg_flops=self.alg_flops_img * N, alg_bytes=self.alg_bytes_img * N + 4.0 * self.wgrad_elems)
             ops.unpack4(scratch.data_ptr(), gw.data_ptr(), self.perm_px8_g)
             return
         lin = self.spec.kind == "linear"

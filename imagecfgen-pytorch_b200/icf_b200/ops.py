@@ -77,7 +77,7 @@ def valid_taps(form, H, P, R, stride, pad):
 
 def conv_forward(dtype, form, N, H, W, Cc, in_pitch, P, Q, K, out_pitch, R, S, stride, pad,
                  src, w, w_rows, w_pitch, dst, bias=None, act="none", slope=0.0, out_f32=False,
-                 mask=None, mask_pitch=0, stats=None, accumulate=False, win=0, alg_flops=None):
+                 mask=None, mask_pitch=0, stats=None, accumulate=False, win=0, alg_flops=None, alg_bytes=None):
     """src/w/dst/bias/mask/stats are raw addresses (ints) or None."""
     a = _l.ConvArgs(dtype, form, N, H, W, Cc, in_pitch, P, Q, K, out_pitch, R, S, stride, pad,
                     w_rows, w_pitch, ACT[act], slope, 1 if out_f32 else 0, mask_pitch,
@@ -90,11 +90,14 @@ def conv_forward(dtype, form, N, H, W, Cc, in_pitch, P, Q, K, out_pitch, R, S, s
         nb = float(es) * (N * (H * W * Cc + P * Q * K) + K * Cc * R * S)
         if alg_flops is not None:
             fl = alg_flops
+        if alg_bytes is not None:
+            nb = alg_bytes
         det = f"{'gather' if form == GATHER else 'transp'} {Cc}x{H}x{W}->{K}x{P}x{Q} k{R}s{stride}p{pad}" + (f" win{win}" if win > 1 else "")
     _launch("icf_conv_forward", _l.load().icf_conv_forward, C.byref(a), flops=fl, nbytes=nb, detail=det)
 
 
-def conv_wgrad(dtype, N, P, Q, A, a_pitch, H, W, B, b_pitch, R, S, stride, pad, small, big, dw, win=0, alg_flops=None):
+def conv_wgrad(dtype, N, P, Q, A, a_pitch, H, W, B, b_pitch, R, S, stride, pad, small, big, dw, win=0, alg_flops=None,
+               alg_bytes=None):
     a = _l.WgradArgs(dtype, N, P, Q, A, a_pitch, H, W, B, b_pitch, R, S, stride, pad, small, big, dw, win)
     fl = nb = 0.0
     if PROFILE is not None:
@@ -103,6 +106,8 @@ def conv_wgrad(dtype, N, P, Q, A, a_pitch, H, W, B, b_pitch, R, S, stride, pad, 
         nb = float(es) * N * (H * W * B + P * Q * A) + 4.0 * A * B * R * S
     if alg_flops is not None:
         fl = alg_flops
+    if alg_bytes is not None:
+        nb = alg_bytes
     det = (f"wgrad A{A}x{P}x{Q} B{B}x{H}x{W} k{R}s{stride}p{pad}" + (f" win{win}" if win > 1 else "")) if PROFILE is not None else ""
     _launch("icf_conv_wgrad", _l.load().icf_conv_wgrad, C.byref(a), flops=fl, nbytes=nb, detail=det)
 
