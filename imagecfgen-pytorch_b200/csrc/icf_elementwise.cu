@@ -784,6 +784,31 @@ __global__ void pack_multi_kernel(const icf_pack_job* __restrict__ jobs) {
   }
 }
 
+__global__ void unpack_multi_kernel(const icf_pack_job* __restrict__ jobs) {
+  const icf_pack_job jb = jobs[blockIdx.y];
+  float* dst = reinterpret_cast<float*>(jb.dst);
+  if (jb.kind == 0) {
+    const icf_perm p = jb.p;
+    const int64_t total = p.d0 * p.d1 * p.d2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t i2 = i % p.d2;
+      const int64_t t = i / p.d2;
+      const int64_t i1 = t % p.d1, i0 = t / p.d1;
+      dst[i0 * p.s0 + i1 * p.s1 + i2 * p.s2] = jb.src[(i0 * p.d1 + i1) * p.d2_pad + i2];
+    }
+  } else {
+    const icf_perm4 p = jb.p4;
+    const int64_t total = p.d0 * p.d1 * p.d2 * p.d3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      int64_t t = i;
+      const int64_t i3 = t % p.d3; t /= p.d3;
+      const int64_t i2 = t % p.d2; t /= p.d2;
+      const int64_t i1 = t % p.d1, i0 = t / p.d1;
+      dst[i0 * p.s0 + i1 * p.s1 + i2 * p.s2 + i3 * p.s3] = jb.src[(i0 * p.d1 + i1) * p.row_pitch + i2 * p.d3_pad + i3];
+    }
+  }
+}
+
 __global__ void unpack_kernel(const float* __restrict__ src, float* dst, const icf_perm p, int atomic_add) {
   const int64_t total = p.d0 * p.d1 * p.d2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -1036,6 +1061,15 @@ int icf_pack_multi(const icf_pack_job* jobs, int32_t n_jobs, int64_t max_elems, 
   if (bx > 64) bx = 64;
   pack_multi_kernel<<<dim3((unsigned)bx, (unsigned)n_jobs), EW_THREADS, 0, icf::as_stream(stream)>>>(jobs);
   return icf::check_launch("pack_multi");
+}
+
+int icf_unpack_multi(const icf_pack_job* jobs, int32_t n_jobs, int64_t max_elems, void* stream) {
+  ICF_REQUIRE(jobs && n_jobs >= 0 && max_elems >= 0, "icf_unpack_multi: bad arguments");
+  if (n_jobs == 0 || max_elems == 0) return 0;
+  int64_t bx = (max_elems + EW_THREADS - 1) / EW_THREADS;
+  if (bx > 64) bx = 64;
+  unpack_multi_kernel<<<dim3((unsigned)bx, (unsigned)n_jobs), EW_THREADS, 0, icf::as_stream(stream)>>>(jobs);
+  return icf::check_launch("unpack_multi");
 }
 
 int icf_unpack(const float* src_packed, float* dst, const icf_perm* p, int32_t atomic_add, void* stream) {

@@ -196,9 +196,21 @@ class LayerExec:
                          self.Hin, self.Win, self.Cin, dx.pitch, self.R, self.S, self.stride, self.pad,
                          dpre.ptr, self.w_bwd.data_ptr(), self.Cin, self.wb_pitch, dx.ptr)
 
-    def wgrad(self, N, dpre: Act, x: Act, gw: torch.Tensor, scratch: torch.Tensor):
-        """gw (checkpoint layout, fp32) = weight gradient; ``scratch`` holds the packed fp32 accumulator."""
+    def unpack_perm(self):
+        """Permutation that takes this layer's packed fp32 weight-gradient accumulator to the checkpoint layout."""
+        if self.fold:
+            return self.perm_fold_g
+        if self.px8:
+            return self.perm_px8_g
+        return self.perm_g
+
+    def wgrad(self, N, dpre: Act, x: Act, gw: Optional[torch.Tensor], scratch: torch.Tensor):
+        """gw (checkpoint layout, fp32) = weight gradient; ``scratch`` holds the packed fp32 accumulator.  With
+        gw = None the caller has zeroed ``scratch`` and unpacks it later (NetExec batches both over all layers)."""
         n = self.wgrad_elems
+        if gw is None:
+            self._wgrad_accumulate(N, dpre, x, scratch)
+            return
         ops.fill_f32(scratch.data_ptr(), 0.0, n)
         if self.fold:
             ops.conv_wgrad(self.code, N, self.P, self.Q, self.Kout, dpre.pitch, self.Hin + 2 * self.pad,
@@ -222,6 +234,28 @@ class LayerExec:
             ops.conv_wgrad(self.code, N, self.P, self.Q, self.Kout, dp_pitch, self.Hin, self.Win, self.Cin,
                            x.pitch, self.R, self.S, self.stride, self.pad, dpre.ptr, x.ptr, scratch.data_ptr())
         ops.unpack(scratch.data_ptr(), gw.data_ptr(), self.perm_g)
+
+    def _wgrad_accumulate(self, N, dpre: Act, x: Act, scratch: torch.Tensor):
+        """The wgrad launch alone: accumulates into the (already zeroed) packed fp32 buffer ``scratch``."""
+        if self.fold:
+            ops.conv_wgrad(self.code, N, self.P, self.Q, self.Kout, dpre.pitch, self.Hin + 2 * self.pad,
+                           self.Win + 2 * self.pad, self.fold * x.pitch, x.pitch, self.R, 1, self.stride, 0, dpre.ptr,
+                           x.ptr, scratch.data_ptr(), win=self.fold, alg_flops=self.alg_flops_img * N,
+                           alg_bytes=self.alg_bytes_img * N + 4.0 * self.wgrad_elems)
+            return
+        if self.px8 and dpre.pitch == 8:
+            ops.conv_wgrad(self.code, N, self.Hin, self.Win, self.Cin, x.pitch, self.P, self.Q, self.S * 8, 8,
+                           self.R, 1, 1, 0, x.ptr, dpre.ptr, scratch.data_ptr(), win=self.S,
+                           alg_flops=self.alg_flops_img * N, alg_bytes=self.alg_bytes_img * N + 4.0 * self.wgrad_elems)
+            return
+        lin = self.spec.kind == "linear"
+        dp_pitch = dpre.pitch * self.Hout * self.Wout if lin else dpre.pitch
+        if self.spec.kind == "convT":     # small = X (A = Cin), big = dY (B = Cout)
+            ops.conv_wgrad(self.code, N, self.Hin, self.Win, self.Cin, x.pitch, self.P, self.Q, self.Kout,
+                           dp_pitch, self.R, self.S, self.stride, self.pad, x.ptr, dpre.ptr, scratch.data_ptr())
+        else:                             # small = dY (A = Cout), big = X (B = Cin)
+            ops.conv_wgrad(self.code, N, self.P, self.Q, self.Kout, dp_pitch, self.Hin, self.Win, self.Cin,
+                           x.pitch, self.R, self.S, self.stride, self.pad, dpre.ptr, x.ptr, scratch.data_ptr())
 
 
 def mask_sites(fam: Family):
@@ -286,6 +320,10 @@ class NetExec:
         self._versions = None
         self._pack_table = None
         self._pack_ptrs = None
+        self._wg_flat = None
+        self._wg_off = None
+        self._wg_table = None
+        self._wg_key = None
         self._scratch = None
         self.emb_key = 2 if role != "G" else 3      # index into fam.cat_attrs tuples
 
@@ -314,6 +352,33 @@ class NetExec:
             self._pack_table, self._pack_ptrs = ops.PackTable(jobs, self.device), ptrs
         self._pack_table.run()                                         # every operand copy of the network, one launch
         self._versions = vers
+
+    # ---- batched weight-gradient plumbing: one zero-fill before, one unpack launch after a whole backward ----------
+    def _wg_layout(self):
+        if self._wg_flat is None:
+            off, self._wg_off = 0, {}
+            for le in self.all_layers():
+                self._wg_off[id(le)] = off
+                off += (le.wgrad_elems + 3) // 4 * 4
+            self._wg_flat = torch.empty(off, dtype=torch.float32, device=self.device)
+        return self._wg_flat
+
+    def wgrad_scratch(self, le):
+        flat = self._wg_layout()
+        o = self._wg_off[id(le)]
+        return flat[o:o + le.wgrad_elems]
+
+    def wgrad_begin(self):
+        flat = self._wg_layout()
+        ops.fill_f32(flat.data_ptr(), 0.0, flat.numel())
+
+    def wgrad_end(self, grads):
+        key = tuple(g.data_ptr() for g in grads.values())
+        if self._wg_table is None or self._wg_key != key:
+            jobs = [(self.wgrad_scratch(le).data_ptr(), grads[le.spec.key + ".weight"].data_ptr(), F32, le.unpack_perm())
+                    for le in self.all_layers()]
+            self._wg_table, self._wg_key = ops.PackTable(jobs, self.device, unpack=True), key
+        self._wg_table.run()
 
     def scratch(self):
         if self._scratch is None:
@@ -439,7 +504,7 @@ class NetExec:
             if grads is not None:
                 if le.perm_bias is not None:
                     ops.unpack(dbias_t.data_ptr(), grads[sp.key + ".bias"].data_ptr(), le.perm_bias)
-                le.wgrad(N, dpre, x, grads[sp.key + ".weight"], self.scratch())
+                le.wgrad(N, dpre, x, None, self.wgrad_scratch(le))
             if i > 0 or need_dx:
                 dx = Act(torch.empty((N * le.Hin * le.Win, x.pitch), dtype=self.dt, device=self.device), le.Cin)
                 le.dgrad(N, dpre, dx)
@@ -525,6 +590,14 @@ class NetExec:
         return out, {"N": N, "feat": fstate, "tower": saved}
 
     def encoder_backward(self, st, dout: Act, grads, need_dX=False):
+        if grads is not None:
+            self.wgrad_begin()
+        r = self._encoder_backward(st, dout, grads, need_dX)
+        if grads is not None:
+            self.wgrad_end(grads)
+        return r
+
+    def _encoder_backward(self, st, dout: Act, grads, need_dX=False):
         N = st["N"]
         need_feat = need_dX or (grads is not None and self.n_emb > 0)
         dfeat = self._tower_bwd("E", N, st["tower"], dout, grads, need_feat, inplace_ok=False)
@@ -550,6 +623,14 @@ class NetExec:
 
     def generator_backward(self, st, dout: Act, grads, need_dz=False, need_dattr=False):
         """-> (dz fp32 [N,latent] | None, [d_onehot per cat attr] | None, [d_cont per cont attr] | None)."""
+        if grads is not None:
+            self.wgrad_begin()
+        r = self._generator_backward(st, dout, grads, need_dz, need_dattr)
+        if grads is not None:
+            self.wgrad_end(grads)
+        return r
+
+    def _generator_backward(self, st, dout: Act, grads, need_dz=False, need_dattr=False):
         N = st["N"]
         need_lat = need_dz or need_dattr or (grads is not None and self.n_emb > 0)
         dlat = self._tower_bwd("G", N, st["tower"], dout, grads, need_lat, inplace_ok=False)
@@ -607,6 +688,14 @@ class NetExec:
 
     def discriminator_backward(self, st, dlogits: Act, grads, need_dX=False, need_dz=False):
         """-> (dX fp32 [N*H*W,1] | None, dz fp32 [N,latent] | None)."""
+        if grads is not None:
+            self.wgrad_begin()
+        r = self._discriminator_backward(st, dlogits, grads, need_dX, need_dz)
+        if grads is not None:
+            self.wgrad_end(grads)
+        return r
+
+    def _discriminator_backward(self, st, dlogits: Act, grads, need_dX=False, need_dz=False):
         N = st["N"]
         fam = self.fam
         kx, kz = fam.Dx[-1].cout, fam.Dz[-1].cout

@@ -91,6 +91,7 @@ _SIGS = {
     "icf_conv_wgrad": (_i32, [C.POINTER(WgradArgs), _vp]),
     "icf_pack": (_i32, [_vp, _vp, _i32, C.POINTER(Perm), _vp]),
     "icf_pack_multi": (_i32, [_vp, _i32, _i64, _vp]),
+    "icf_unpack_multi": (_i32, [_vp, _i32, _i64, _vp]),
     "icf_unpack": (_i32, [_vp, _vp, C.POINTER(Perm), _i32, _vp]),
     "icf_pack4": (_i32, [_vp, _vp, _i32, C.POINTER(Perm4), _vp]),
     "icf_unpack4": (_i32, [_vp, _vp, C.POINTER(Perm4), _vp]),

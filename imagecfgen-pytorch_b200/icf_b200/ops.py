@@ -123,18 +123,20 @@ def pack(src, dst, dst_dtype, perm):
 class PackTable:
     """Device-resident table of re-packing jobs (icf_pack_job[]) launched as one kernel by ``run``."""
 
-    def __init__(self, jobs, device):
-        """jobs: list of (src_ptr, dst_ptr, dst_dtype, perm) with perm an icf_perm or icf_perm4."""
+    def __init__(self, jobs, device, unpack=False):
+        """jobs: list of (src_ptr, dst_ptr, dst_dtype, perm) with perm an icf_perm or icf_perm4; ``unpack``: the table
+        is for icf_unpack_multi (packed fp32 accumulators -> checkpoint-layout gradients)."""
         arr = (_l.PackJob * len(jobs))()
         self.max_elems = 0
+        self.unpack = unpack
         for j, (src, dst, dt, perm) in zip(arr, jobs):
             j.src, j.dst, j.dst_dtype = src, dst, dt
             if isinstance(perm, _l.Perm4):
                 j.kind, j.p4 = 1, perm
-                n = perm.d0 * perm.d1 * perm.row_pitch
+                n = perm.d0 * perm.d1 * (perm.d2 * perm.d3 if unpack else perm.row_pitch)
             else:
                 j.kind, j.p = 0, perm
-                n = perm.d0_pad * perm.d1 * perm.d2_pad
+                n = perm.d0 * perm.d1 * perm.d2 if unpack else perm.d0_pad * perm.d1 * perm.d2_pad
             self.max_elems = max(self.max_elems, n)
         self.n = len(jobs)
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8) if self.n else torch.zeros(0, dtype=torch.uint8)
@@ -142,7 +144,8 @@ class PackTable:
 
     def run(self):
         if self.n:
-            _launch("icf_pack_multi", _l.load().icf_pack_multi, self.dev.data_ptr(), self.n, self.max_elems)
+            fn = _l.load().icf_unpack_multi if self.unpack else _l.load().icf_pack_multi
+            _launch("icf_unpack_multi" if self.unpack else "icf_pack_multi", fn, self.dev.data_ptr(), self.n, self.max_elems)
 
 
 def make_perm4(d0, d1, d2, d3, s0, s1, s2, s3, d3_pad, row_pitch):

@@ -135,6 +135,9 @@ typedef struct icf_pack_job {
   icf_perm4 p4;
 } icf_pack_job;
 int icf_pack_multi(const icf_pack_job* jobs, int32_t n_jobs, int64_t max_elems, void* stream);
+/* The reverse for gradients: every job copies its packed fp32 accumulator (src) into the checkpoint-layout gradient
+ * (dst, assignment), icf_unpack / icf_unpack4 semantics; dst_dtype is ignored. */
+int icf_unpack_multi(const icf_pack_job* jobs, int32_t n_jobs, int64_t max_elems, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Attribute / latent feature assembly (mnist.py:47-55,77-85; audio_mnist.py:204-210,250-256).
