@@ -1057,8 +1057,8 @@ int icf_pack(const float* src, void* dst, int32_t dst_dtype, const icf_perm* p, 
 int icf_pack_multi(const icf_pack_job* jobs, int32_t n_jobs, int64_t max_elems, void* stream) {
   ICF_REQUIRE(jobs && n_jobs >= 0 && max_elems >= 0, "icf_pack_multi: bad arguments");
   if (n_jobs == 0 || max_elems == 0) return 0;
-  int64_t bx = (max_elems + EW_THREADS - 1) / EW_THREADS;
-  if (bx > 64) bx = 64;
+  int64_t bx = (max_elems + 4 * EW_THREADS - 1) / (4 * EW_THREADS);   // ~4 elements per thread of the largest job
+  if (bx > 1024) bx = 1024;
   pack_multi_kernel<<<dim3((unsigned)bx, (unsigned)n_jobs), EW_THREADS, 0, icf::as_stream(stream)>>>(jobs);
   return icf::check_launch("pack_multi");
 }
@@ -1066,8 +1066,8 @@ int icf_pack_multi(const icf_pack_job* jobs, int32_t n_jobs, int64_t max_elems, 
 int icf_unpack_multi(const icf_pack_job* jobs, int32_t n_jobs, int64_t max_elems, void* stream) {
   ICF_REQUIRE(jobs && n_jobs >= 0 && max_elems >= 0, "icf_unpack_multi: bad arguments");
   if (n_jobs == 0 || max_elems == 0) return 0;
-  int64_t bx = (max_elems + EW_THREADS - 1) / EW_THREADS;
-  if (bx > 64) bx = 64;
+  int64_t bx = (max_elems + 4 * EW_THREADS - 1) / (4 * EW_THREADS);
+  if (bx > 1024) bx = 1024;
   unpack_multi_kernel<<<dim3((unsigned)bx, (unsigned)n_jobs), EW_THREADS, 0, icf::as_stream(stream)>>>(jobs);
   return icf::check_launch("unpack_multi");
 }
