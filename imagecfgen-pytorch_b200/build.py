@@ -26,6 +26,8 @@ def build(force=False, verbose=False):
            "--use_fast_math" if os.environ.get("ICF_FAST_MATH") else "-DICF_PRECISE_MATH",
            "-Xcompiler", "-fPIC,-O2", "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
            "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    if os.environ.get("ICF_WS_INSTRUMENT"):
+        cmd.insert(1, "-DICF_WS_INSTRUMENT")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

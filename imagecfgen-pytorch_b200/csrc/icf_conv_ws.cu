@@ -82,7 +82,10 @@ struct WsParams {
 
 // KD > 0: C spans KD 16-wide MMA steps (<= 8, i.e. up to two 64-channel chunks), issue loop fully unrolled;
 // KD == 0: generic
-#define WS_TIMED_WAIT(counter, bar, par)                    \
+// Per-role cycle counters (CTA 0) are a build-time option: `ICF_WS_INSTRUMENT=1 python build.py --force`, then run with
+// ICF_WS_DEBUG=1.  The production issue loop must stay small enough for the L0 instruction cache.
+#ifdef ICF_WS_INSTRUMENT
+#define WS_TIMED_WAIT(counter, bar, par)                   \
   do {                                                     \
     if (dbg_on) {                                          \
       const long long t_ = clock64();                      \
@@ -92,6 +95,9 @@ struct WsParams {
       mbar_wait(bar, par);                                 \
     }                                                      \
   } while (0)
+#else
+#define WS_TIMED_WAIT(counter, bar, par) mbar_wait(bar, par)
+#endif
 
 template <int TILE_N, int KD>
 __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_constant__ CUtensorMap map_a,
@@ -145,7 +151,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t slab_addr = smem_u32(wslab), slots_addr = smem_u32(slots);
+#ifdef ICF_WS_INSTRUMENT
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
+#else
+  constexpr bool dbg_on = false;
+#endif
   long long w0 = 0, w1 = 0;                 // cycles spent in this role's two kinds of barrier waits
   const long long t_begin = dbg_on ? clock64() : 0;
   const uint32_t W_BLOCK = (uint32_t)TILE_N * (uint32_t)p.rowb;      // one (tap, K chunk) block of the weight slab
@@ -200,6 +210,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         WS_TIMED_WAIT(w0, slot_full(s), ph);
         tc_fence_after();
         const uint32_t a_lo0 = (((slots_addr + (uint32_t)s * p.slot_bytes) >> 4) & 0x3FFFu) | lbo_lo;
+#pragma unroll 1                                   // keep the issue loop small: it has to live in the L0 instruction cache
         for (int gi = 0; gi < ngroups; ++gi) {
           const int dy = cl.grp[gi].dy;
           const int num = y - dy;
@@ -214,6 +225,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
           }
           const uint32_t d_tmem = tmem_base + (uint32_t)acc * TILE_N;
           const int t0 = cl.grp[gi].first, t1 = t0 + cl.grp[gi].count;
+#pragma unroll 1
           for (int t = t0; t < t1; ++t) {
             const uint32_t a_lo = a_lo0 + cl.taps[t].a_off16;
             const uint32_t b_lo = b_lo0 + (uint32_t)(t * p.kchunks) * WB16;
