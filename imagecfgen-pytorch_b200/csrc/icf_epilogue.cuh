@@ -8,6 +8,18 @@
 
 namespace icf_tc {
 
+// LeakyReLU in two instructions (FMUL + FMNMX) for the slopes the models use (0 <= slope <= 1: max(x, slope*x));
+// the generic select otherwise.  NaN propagates through both.
+__device__ __forceinline__ void lrelu16(float (&f)[16], float slope) {
+  if (slope >= 0.f && slope <= 1.f) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], f[j] * slope);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * slope;
+  }
+}
+
 // `o` points at channel `kbase` of the destination pixel; nvalid = channels of this group that exist (1..16);
 // npad >= nvalid = channels that may be WRITTEN (the pitch padding up to the next multiple of 8 is stored as zeros
 // so that a ragged channel count still leaves as 16-byte stores)
@@ -17,8 +29,7 @@ __device__ __forceinline__ void epi16(const uint32_t (&v)[16], const float* sbia
 #pragma unroll
   for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + sbias[j];
   if (act == ICF_ACT_LRELU) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * slope;
+    lrelu16(f, slope);
   } else if (act == ICF_ACT_TANH) {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
@@ -68,8 +79,7 @@ __device__ __forceinline__ void epi16_pack(const uint32_t (&v)[16], const float*
 #pragma unroll
   for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + sbias[j];
   if (act == ICF_ACT_LRELU) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * slope;
+    lrelu16(f, slope);
   } else if (act == ICF_ACT_TANH) {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
