@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(VT) scale_shift_mask_v8(const void* y, int ydt
   }
 }
 
-__global__ void __launch_bounds__(VT) bn_bwd_reduce_v8(const void* dU, int ddt, int dpitch, const void* y, int ydt, int ypitch,
+__global__ void __launch_bounds__(VT, 3) bn_bwd_reduce_v8(const void* dU, int ddt, int dpitch, const void* y, int ydt, int ypitch,
                                                        int64_t pixels, int pps, int C, const float* mask, int mpitch,
                                                        const float* mean, const float* invstd, float* sums) {
   __shared__ float sm[2 * VSM];
@@ -532,9 +532,9 @@ __global__ void __launch_bounds__(VT) bn_bwd_reduce_v8(const void* dU, int ddt, 
         for (int j = 0; j < 8; ++j) g.v[j] *= mk.v[j];
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 8; ++j) {        // raw moments; sum g*xhat = invstd*(sum g*y - mean*sum g) is applied once below
         acc[0][j] += g.v[j];
-        acc[1][j] = fmaf(g.v[j], (yv.v[j] - mu.v[j]) * is.v[j], acc[1][j]);
+        acc[1][j] = fmaf(g.v[j], yv.v[j], acc[1][j]);
       }
     };
     if (ddt == ICF_BF16 && ydt == ICF_BF16) {
@@ -558,6 +558,8 @@ __global__ void __launch_bounds__(VT) bn_bwd_reduce_v8(const void* dU, int ddt, 
       for (int64_t pix = m.pix0; pix < pixels; pix += m.pstride)
         process(pix, ld8(dU, ddt, pix * dpitch + m.c0), ld8(y, ydt, pix * ypitch + m.c0));
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[1][j] = is.v[j] * (acc[1][j] - mu.v[j] * acc[0][j]);
   }
   float* dst[2] = {sums, sums + C};
   flush_partials<2>(acc, m.cbase_block, m.c0, C, m.span, dst, sm);
@@ -580,7 +582,7 @@ __global__ void __launch_bounds__(VT) col_stats_v8(const void* y, int ydt, int y
   flush_partials<2>(acc, m.cbase_block, m.c0, C, m.span, dst, sm);
 }
 
-__global__ void __launch_bounds__(VT) act_backward_v8(const icf_actbwd_args a) {
+__global__ void __launch_bounds__(VT, 3) act_backward_v8(const icf_actbwd_args a) {
   __shared__ float sm[VSM];
   const VMap m = vmap(a.C, a.pixels);
   float acc[1][8];
@@ -588,14 +590,20 @@ __global__ void __launch_bounds__(VT) act_backward_v8(const icf_actbwd_args a) {
   for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
   if (m.c0 < a.C) {
     const bool bn = a.bn_sums != nullptr;
-    V8 gs, m0, m1, mu, is;
+    // BatchNorm backward folded into one affine form per channel:
+    //   gamma*invstd*(g - m0 - (y - mu)*invstd*m1)  =  cA*g + cB*y + cC
+    V8 cA, cB, cC;
     if (bn) {
       const float invM = 1.f / (float)a.pixels;
-      mu = ldf8(a.bn_mean + m.c0);
-      is = ldf8(a.bn_invstd + m.c0);
+      const V8 mu = ldf8(a.bn_mean + m.c0), is = ldf8(a.bn_invstd + m.c0);
       const V8 ga = ldf8(a.bn_gamma + m.c0), s0 = ldf8(a.bn_sums + m.c0), s1 = ldf8(a.bn_sums + a.C + m.c0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { gs.v[j] = ga.v[j] * is.v[j]; m0.v[j] = s0.v[j] * invM; m1.v[j] = s1.v[j] * invM; }
+      for (int j = 0; j < 8; ++j) {
+        const float gs = ga.v[j] * is.v[j], m0 = s0.v[j] * invM, m1 = s1.v[j] * invM;
+        cA.v[j] = gs;
+        cB.v[j] = -gs * is.v[j] * m1;
+        cC.v[j] = gs * (mu.v[j] * is.v[j] * m1 - m0);
+      }
       if (m.pix0 == 0) {            // exactly one thread per channel group has pix0 == 0
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -613,7 +621,7 @@ __global__ void __launch_bounds__(VT) act_backward_v8(const icf_actbwd_args a) {
           for (int j = 0; j < 8; ++j) g.v[j] *= mk.v[j];
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g.v[j] = gs.v[j] * (g.v[j] - m0.v[j] - (yv.v[j] - mu.v[j]) * is.v[j] * m1.v[j]);
+        for (int j = 0; j < 8; ++j) g.v[j] = fmaf(cA.v[j], g.v[j], fmaf(cB.v[j], yv.v[j], cC.v[j]));
       }
       if (a.out_mask) {
         const V8 mk = ldf8(a.out_mask + n * a.mask_pitch + m.c0);
