@@ -463,7 +463,10 @@ __device__ __forceinline__ void flush_partials(float (*acc)[8], int cbase_block,
 }
 
 // thread -> (channel group, first pixel, pixel stride).  cg = C/8 groups; a block covers min(cg, VT) groups.
-struct VMap { int c0, cbase_block, span; int64_t pix0, pstride; };
+// Each block owns a CONTIGUOUS range of pixel rows [.., pix_end) and walks it `rows` pixels at a time, so a thread stays
+// inside one image for many iterations: the sample index (a division) and the per-(sample, channel) Dropout2d mask
+// values are refreshed only when the image changes (MaskCache).
+struct VMap { int c0, cbase_block, span; int64_t pix0, pstride, pix_end; };
 __device__ __forceinline__ VMap vmap(int C, int64_t pixels) {
   const int cg = C >> 3;
   const int gpb = cg < VT ? cg : VT;                  // channel groups per block
@@ -475,11 +478,25 @@ __device__ __forceinline__ VMap vmap(int C, int64_t pixels) {
   m.cbase_block = cb * gpb * 8;
   m.span = gpb * 8;
   m.c0 = m.cbase_block + (threadIdx.x % gpb) * 8;
-  m.pix0 = pb * rows + threadIdx.x / gpb;
-  m.pstride = npb * rows;
+  int64_t chunk = (pixels + npb - 1) / npb;
+  chunk = (chunk + rows - 1) / rows * rows;
+  m.pix0 = pb * chunk + threadIdx.x / gpb;
+  m.pstride = rows;
+  m.pix_end = (pb + 1) * chunk < pixels ? (pb + 1) * chunk : pixels;
   if ((int)threadIdx.x / gpb >= rows) m.c0 = 1 << 30;   // leftover threads when gpb does not divide the block
   return m;
 }
+struct MaskCache { int64_t lo = 1, hi = 0; V8 v; };
+__device__ __forceinline__ const V8& cached_mask(MaskCache& mc, const float* mask, int64_t pitch, int64_t pix, int pps, int c0) {
+  if (pix < mc.lo || pix >= mc.hi) {
+    const int64_t n = sample_of(pix, pps);
+    mc.lo = n * pps;
+    mc.hi = mc.lo + pps;
+    mc.v = ldf8(mask + n * pitch + c0);
+  }
+  return mc.v;
+}
+
 inline int vgrid(int C, int64_t pixels) {
   const int cg = C >> 3;
   const int gpb = cg < VT ? cg : VT;
@@ -500,14 +517,15 @@ __global__ void __launch_bounds__(VT) scale_shift_mask_v8(const void* y, int ydt
   V8 sc, sh;
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc.v[j] = scale ? scale[m.c0 + j] : 1.f; sh.v[j] = (scale && shift) ? shift[m.c0 + j] : 0.f; }
-  for (int64_t pix = m.pix0; pix < pixels; pix += m.pstride) {
+  MaskCache mc;
+  for (int64_t pix = m.pix0; pix < m.pix_end; pix += m.pstride) {
     V8 v = ld8(y, ydt, pix * ypitch + m.c0);
     if (scale) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v.v[j] = fmaf(v.v[j], sc.v[j], sh.v[j]);
     }
     if (mask) {
-      const V8 mk = ldf8(mask + sample_of(pix, pps) * mpitch + m.c0);
+      const V8& mk = cached_mask(mc, mask, mpitch, pix, pps, m.c0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v.v[j] *= mk.v[j];
     }
@@ -525,9 +543,10 @@ __global__ void __launch_bounds__(VT, 3) bn_bwd_reduce_v8(const void* dU, int dd
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
   if (m.c0 < C) {
     const V8 mu = ldf8(mean + m.c0), is = ldf8(invstd + m.c0);
+    MaskCache mc;
     auto process = [&](int64_t pix, V8 g, const V8& yv) {
       if (mask) {
-        const V8 mk = ldf8(mask + sample_of(pix, pps) * mpitch + m.c0);
+        const V8& mk = cached_mask(mc, mask, mpitch, pix, pps, m.c0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) g.v[j] *= mk.v[j];
       }
@@ -538,12 +557,12 @@ __global__ void __launch_bounds__(VT, 3) bn_bwd_reduce_v8(const void* dU, int dd
       }
     };
     if (ddt == ICF_BF16 && ydt == ICF_BF16) {
-      for (int64_t pix = m.pix0; pix < pixels; pix += VU * m.pstride) {
+      for (int64_t pix = m.pix0; pix < m.pix_end; pix += VU * m.pstride) {
         uint4 gr[VU], yr[VU];
 #pragma unroll
         for (int u = 0; u < VU; ++u) {
           const int64_t pu = pix + u * m.pstride;
-          if (pu < pixels) {
+          if (pu < m.pix_end) {
             gr[u] = ldraw8(dU, pu * dpitch + m.c0);
             yr[u] = ldraw8(y, pu * ypitch + m.c0);
           }
@@ -551,11 +570,11 @@ __global__ void __launch_bounds__(VT, 3) bn_bwd_reduce_v8(const void* dU, int dd
 #pragma unroll
         for (int u = 0; u < VU; ++u) {
           const int64_t pu = pix + u * m.pstride;
-          if (pu < pixels) process(pu, cvt8(gr[u]), cvt8(yr[u]));
+          if (pu < m.pix_end) process(pu, cvt8(gr[u]), cvt8(yr[u]));
         }
       }
     } else {
-      for (int64_t pix = m.pix0; pix < pixels; pix += m.pstride)
+      for (int64_t pix = m.pix0; pix < m.pix_end; pix += m.pstride)
         process(pix, ld8(dU, ddt, pix * dpitch + m.c0), ld8(y, ydt, pix * ypitch + m.c0));
     }
 #pragma unroll
@@ -572,7 +591,7 @@ __global__ void __launch_bounds__(VT) col_stats_v8(const void* y, int ydt, int y
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
   if (m.c0 < C) {
-    for (int64_t pix = m.pix0; pix < pixels; pix += m.pstride) {
+    for (int64_t pix = m.pix0; pix < m.pix_end; pix += m.pstride) {
       const V8 v = ld8(y, ydt, pix * ypitch + m.c0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { acc[0][j] += v.v[j]; acc[1][j] = fmaf(v.v[j], v.v[j], acc[1][j]); }
@@ -582,7 +601,7 @@ __global__ void __launch_bounds__(VT) col_stats_v8(const void* y, int ydt, int y
   flush_partials<2>(acc, m.cbase_block, m.c0, C, m.span, dst, sm);
 }
 
-__global__ void __launch_bounds__(VT, 3) act_backward_v8(const icf_actbwd_args a) {
+__global__ void __launch_bounds__(VT, 2) act_backward_v8(const icf_actbwd_args a) {
   __shared__ float sm[VSM];
   const VMap m = vmap(a.C, a.pixels);
   float acc[1][8];
@@ -612,11 +631,11 @@ __global__ void __launch_bounds__(VT, 3) act_backward_v8(const icf_actbwd_args a
         }
       }
     }
+    MaskCache mc_bn, mc_out;
     auto process = [&](int64_t pix, V8 g, const V8& yv) {
-      const int64_t n = sample_of(pix, a.pixels_per_sample);
       if (bn) {
         if (a.bn_mask) {
-          const V8 mk = ldf8(a.bn_mask + n * a.bn_mask_pitch + m.c0);
+          const V8& mk = cached_mask(mc_bn, a.bn_mask, a.bn_mask_pitch, pix, a.pixels_per_sample, m.c0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) g.v[j] *= mk.v[j];
         }
@@ -624,7 +643,7 @@ __global__ void __launch_bounds__(VT, 3) act_backward_v8(const icf_actbwd_args a
         for (int j = 0; j < 8; ++j) g.v[j] = fmaf(cA.v[j], g.v[j], fmaf(cB.v[j], yv.v[j], cC.v[j]));
       }
       if (a.out_mask) {
-        const V8 mk = ldf8(a.out_mask + n * a.mask_pitch + m.c0);
+        const V8& mk = cached_mask(mc_out, a.out_mask, a.mask_pitch, pix, a.pixels_per_sample, m.c0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) g.v[j] *= mk.v[j];
       }
@@ -637,12 +656,12 @@ __global__ void __launch_bounds__(VT, 3) act_backward_v8(const icf_actbwd_args a
     };
     if (a.d_dtype == ICF_BF16 && a.y_dtype == ICF_BF16) {
       // raw 16-byte loads of VU pixels first, math afterwards: enough bytes in flight at 2-3 blocks per SM
-      for (int64_t pix = m.pix0; pix < a.pixels; pix += VU * m.pstride) {
+      for (int64_t pix = m.pix0; pix < m.pix_end; pix += VU * m.pstride) {
         uint4 gr[VU], yr[VU];
 #pragma unroll
         for (int u = 0; u < VU; ++u) {
           const int64_t pu = pix + u * m.pstride;
-          if (pu < a.pixels) {
+          if (pu < m.pix_end) {
             gr[u] = ldraw8(a.dOut, pu * a.d_pitch + m.c0);
             yr[u] = ldraw8(a.y, pu * a.y_pitch + m.c0);
           }
@@ -650,11 +669,11 @@ __global__ void __launch_bounds__(VT, 3) act_backward_v8(const icf_actbwd_args a
 #pragma unroll
         for (int u = 0; u < VU; ++u) {
           const int64_t pu = pix + u * m.pstride;
-          if (pu < a.pixels) process(pu, cvt8(gr[u]), cvt8(yr[u]));
+          if (pu < m.pix_end) process(pu, cvt8(gr[u]), cvt8(yr[u]));
         }
       }
     } else {
-      for (int64_t pix = m.pix0; pix < a.pixels; pix += m.pstride)
+      for (int64_t pix = m.pix0; pix < m.pix_end; pix += m.pstride)
         process(pix, ld8(a.dOut, a.d_dtype, pix * a.d_pitch + m.c0), ld8(a.y, a.y_dtype, pix * a.y_pitch + m.c0));
     }
   }
