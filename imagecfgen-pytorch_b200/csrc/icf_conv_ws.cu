@@ -542,7 +542,9 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   double best = 1e30;
   for (int xg = 1; xg <= 16; xg *= 2) {
     const double eff = (double)max_q / (icf::cdiv(max_q, xg) * xg);
-    const double cost = (1.0 / eff) * (1.0 + 0.25 * brange / xg);
+    // wasted MMA rows (1/eff) against x-halo re-fetch; stride-2 gathers load two parity sub-rows per source row and
+    // measured better with wide columns (G.layers.6 dgrad: XG 16 beats XG 2 by 25 %)
+    const double cost = (1.0 / eff) * (1.0 + (q.sstep == 2 ? 0.5 : 0.25) * brange / xg);
     if (cost < best - 1e-9 || (cost < best + 1e-9 && xg > q.XG)) { best = cost; q.XG = xg; }
   }
   {
