@@ -78,6 +78,10 @@ int icf_conv_forward(const icf_conv_args* a, void* stream) {
   cudaStream_t st = icf::as_stream(stream);
   if (a->dtype == ICF_BF16 && icf_tc_enabled()) {
     static const bool ws_on = []() { const char* e = getenv("ICF_DISABLE_WS"); return !(e && e[0] && e[0] != '0'); }();
+    {
+      int r = icf_sc_conv_forward(a, st);     // scatter-form transposed conv for <= 8 output channels (taps in the MMA N)
+      if (r >= 0) { icf::g_conv_path = ICF_PATH_SC; return r; }
+    }
     if (ws_on) {
       int r = icf_ws_conv_forward(a, st);     // weight-stationary row-streaming kernel (small weight slabs)
       if (r >= 0) { icf::g_conv_path = ICF_PATH_WS; return r; }

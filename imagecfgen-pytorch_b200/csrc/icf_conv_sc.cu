@@ -1,0 +1,263 @@
+// Scatter-form transposed convolution for FEW output channels (sm_100a: tcgen05 / TMEM / TMA).
+//
+//   out[n, y+r, x+s, k] += sum_c in[n, y, x, c] * w[k][r*S+s][c]        stride 1, no padding, K <= 8, W+S-1 <= 32
+//
+// (the Cout = 1 generator tail `G.layers.8`, and the data gradient of the 5-channel first discriminator layer).  A
+// gather-form implicit GEMM needs R*S*ceil(C/16) MMAs of N = 16 per 128 output pixels and is bound by the shared-
+// memory reads of its A operand.  Here the taps move into the N dimension instead:
+//     T[pixel][(k, tap)] = sum_c in[pixel][c] * w[k][tap][c]            ONE MMA chain of N = 8*taps per source row
+// and the col2im (out[y+r][x+s] += T[y][x][tap]) happens in the epilogue REGISTERS: a tile is 4 images x 32 x-lanes
+// ordered [image][x], so an epilogue warp owns one image row, the shift by s is a __shfl_up, the R partially summed
+// output rows slide through registers, and every finished row leaves as one coalesced store per warp.
+// ceil(C/16) MMAs per source row of 4 images instead of R*S*ceil(C/16) per 128 output pixels.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer (+TMEM), warps 2..5 epilogue (warp = image).
+#include "icf_epilogue.cuh"
+
+#include <cstdlib>
+#include <cstring>
+
+namespace {
+
+using namespace icf_tc;
+
+constexpr int SC_THREADS = 192, SC_SLOTS = 8, SC_ACC_COLS = 256;
+
+struct ScParams {
+  int N, H, W, C, K, P, Q, out_pitch;
+  int taps, TP;                 // real taps, taps padded so that 8*TP is a multiple of 16
+  int kdepth;                   // 16-wide K steps
+  int tiles;                    // ceil(N / 4)
+  uint32_t w_bytes;             // weight tile: 8*TP rows of 128 B
+  int act;
+  float slope;
+  int out_f32, mask_pitch;
+  const float* bias;
+  const float* mask;
+  void* dst;
+};
+
+template <int R, int S, int KT>
+__global__ void __launch_bounds__(SC_THREADS, 1) conv_sc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_w,
+                                                                const __grid_constant__ ScParams p) {
+  constexpr uint32_t SLOT_BYTES = 128 * 128;                      // [4 images][32 x][64 ch]
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wtile = smem;
+  uint8_t* slots = smem + ((p.w_bytes + 1023u) & ~1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slots + SC_SLOTS * SLOT_BYTES);   // full[8] empty[8] acc_full[2] acc_empty[2] w
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SC_SLOTS + 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (SC_SLOTS + s); };
+  auto acc_full = [&](int b) { return bar_base + 8u * (2 * SC_SLOTS + b); };
+  auto acc_empty = [&](int b) { return bar_base + 8u * (2 * SC_SLOTS + 2 + b); };
+  const uint32_t w_bar = bar_base + 8u * (2 * SC_SLOTS + 4);
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_w);
+    for (int s = 0; s < SC_SLOTS; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 4);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<2 * SC_ACC_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, p.w_bytes);
+      tma_load_3d(smem_u32(wtile), &map_w, w_bar, 0, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x)
+        for (int y = 0; y < p.H; ++y) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), SLOT_BYTES);
+          tma_load_4d(smem_u32(slots) + (uint32_t)s * SLOT_BYTES, &map_a, full_bar(s), 0, 0, y, tile * 4);
+          if (++s == SC_SLOTS) { s = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, 8 * p.TP, 0, 0);
+      mbar_wait(w_bar, 0);
+      tc_fence_after();
+      const uint64_t bdesc = make_desc(smem_u32(wtile), 16, 1024);
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t g = 0;                                   // source rows issued so far
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x)
+        for (int y = 0; y < p.H; ++y, ++g) {
+          const uint32_t buf = g & 1u;
+          mbar_wait(acc_empty(buf), ((g >> 1) & 1u) ^ 1u);
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint64_t adesc = make_desc(smem_u32(slots) + (uint32_t)s * SLOT_BYTES, 16, 1024);
+          for (int k = 0; k < p.kdepth; ++k) umma_bf16(tmem_base + buf * SC_ACC_COLS, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : 0u);
+          umma_commit(empty_bar(s));
+          umma_commit(acc_full(buf));
+          if (++s == SC_SLOTS) { s = 0; ph ^= 1; }
+        }
+    }
+  } else {
+    // ===== epilogue: warp = image of the tile, lane = x =====
+    const int q4 = warp & 3;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const int esize = p.out_f32 ? 4 : 2;
+    float bias[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) bias[k] = (p.bias && k < p.K) ? __ldg(p.bias + k) : 0.f;
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      const int n = tile * 4 + q4;
+      const bool store = n < p.N && lane < p.Q;
+      float mk[KT];
+#pragma unroll
+      for (int k = 0; k < KT; ++k) mk[k] = (p.mask && n < p.N && k < p.K) ? __ldg(p.mask + (int64_t)n * p.mask_pitch + k) : 1.f;
+      float win[R][KT];                                 // partially summed output rows y .. y+R-1 of this thread's column
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int k = 0; k < KT; ++k) win[r][k] = 0.f;
+      auto emit = [&](int y_out) {                      // finished output row: bias + activation + mask, one store per pixel
+        if (!store) return;
+        float f[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          float x = win[0][k] + bias[k];
+          if (p.act == ICF_ACT_LRELU) x = x > 0.f ? x : x * p.slope;
+          else if (p.act == ICF_ACT_TANH) { if (k < p.K) x = tanhf(x); }
+          f[k] = k < p.K ? x * mk[k] : 0.f;
+        }
+        uint8_t* o = reinterpret_cast<uint8_t*>(p.dst) + (((int64_t)n * p.P + y_out) * p.Q + lane) * p.out_pitch * esize;
+        if (p.out_f32) {
+#pragma unroll
+          for (int k = 0; k < KT; ++k)
+            if (k < p.K) reinterpret_cast<float*>(o)[k] = f[k];
+        } else if (KT == 8 && p.out_pitch >= 8 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+          uint4 w4;                                     // pitch padding is written as zeros
+          w4.x = pack_bf16(f[0], f[KT > 1 ? 1 : 0]); w4.y = pack_bf16(f[KT > 2 ? 2 : 0], f[KT > 3 ? 3 : 0]);
+          w4.z = pack_bf16(f[KT > 4 ? 4 : 0], f[KT > 5 ? 5 : 0]); w4.w = pack_bf16(f[KT > 6 ? 6 : 0], f[KT > 7 ? 7 : 0]);
+          *reinterpret_cast<uint4*>(o) = w4;
+        } else {
+#pragma unroll
+          for (int k = 0; k < KT; ++k)
+            if (k < p.K) reinterpret_cast<__nv_bfloat16*>(o)[k] = __float2bfloat16_rn(f[k]);
+        }
+      };
+      auto slide = [&]() {
+#pragma unroll
+        for (int r = 0; r + 1 < R; ++r)
+#pragma unroll
+          for (int k = 0; k < KT; ++k) win[r][k] = win[r + 1][k];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) win[R - 1][k] = 0.f;
+      };
+      for (int y = 0; y < p.H; ++y, ++g) {
+        const uint32_t buf = g & 1u;
+        mbar_wait(acc_full(buf), (g >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          if (k < p.K) {
+            constexpr int NCH = (R * S + 15) / 16;      // 16-column chunks of this channel's taps: all loaded, one wait
+            uint32_t v[NCH][16];
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) tmem_ld16(lane_addr + buf * SC_ACC_COLS + (uint32_t)(k * p.TP + ch * 16), v[ch]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int tap = 0; tap < R * S; ++tap) {
+              const int r = tap / S, s = tap % S;
+              const float t = __shfl_up_sync(0xffffffffu, __uint_as_float(v[tap / 16][tap % 16]), s);
+              if (lane >= s) win[r][k] += t;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(buf));
+        emit(y);                                        // row y has received its last contribution (tap row 0)
+        slide();
+      }
+#pragma unroll
+      for (int r = 0; r + 1 < R; ++r) {                 // the R-1 rows below the last source row
+        emit(p.H + r);
+        slide();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<2 * SC_ACC_COLS>(tmem_base);
+}
+
+template <int R, int S, int KT>
+int launch_sc(const CUtensorMap& ma, const CUtensorMap& mw, const ScParams& p, int grid, size_t smem, cudaStream_t st) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_sc_kernel<R, S, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ICF_REQUIRE(e == cudaSuccess, "scatter-form conv: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+    configured = smem;
+  }
+  conv_sc_kernel<R, S, KT><<<grid, SC_THREADS, smem, st>>>(ma, mw, p);
+  return icf::check_launch("conv_sc");
+}
+
+}  // namespace
+
+// returns 0 = launched, -1 = not this kernel's case, >0 = error
+int icf_sc_conv_forward(const icf_conv_args* a, cudaStream_t st) {
+  if (a->dtype != ICF_BF16 || a->accumulate || a->form != ICF_FORM_TRANSPOSED || a->stride != 1 || a->pad != 0) return -1;
+  if (a->K > 8 || a->C > 64 || a->R != a->S || (a->R != 4 && a->R != 5) || a->win > 1 || a->stats) return -1;
+  if (a->W + a->S - 1 > 32 || a->Q != a->W + a->S - 1 || a->P != a->H + a->R - 1) return -1;
+  if ((a->in_pitch & 7) || (a->w_pitch & 7)) return -1;
+  if ((reinterpret_cast<uintptr_t>(a->src) & 15) || (reinterpret_cast<uintptr_t>(a->w) & 15)) return -1;
+  static const bool off = []() { const char* e = getenv("ICF_DISABLE_SC"); return e && e[0] && e[0] != '0'; }();
+  if (off) return -1;
+  ScParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = a->N; p.H = a->H; p.W = a->W; p.C = a->C; p.K = a->K; p.P = a->P; p.Q = a->Q; p.out_pitch = a->out_pitch;
+  p.taps = a->R * a->S;
+  p.TP = (p.taps + 1) & ~1;
+  if (8 * p.TP > SC_ACC_COLS) return -1;
+  p.kdepth = icf::cdiv(a->C, 16);
+  p.tiles = icf::cdiv(a->N, 4);
+  p.w_bytes = (uint32_t)(8 * p.TP) * 128u;
+  p.act = a->act; p.slope = a->slope; p.out_f32 = a->out_f32; p.mask_pitch = a->mask_pitch;
+  p.bias = a->bias; p.mask = a->out_mask; p.dst = a->dst;
+  CUtensorMap ma, mw;
+  {
+    // [N][H][W][C] read as boxes {64 ch, 32 x, 1 row, 4 images}: tile rows ordered [image][x]
+    cuuint64_t dims[4] = {(cuuint64_t)a->C, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N};
+    cuuint64_t str[3] = {(cuuint64_t)a->in_pitch * 2, (cuuint64_t)a->W * a->in_pitch * 2, (cuuint64_t)a->H * a->W * a->in_pitch * 2};
+    cuuint32_t box[4] = {64, 32, 1, 4};
+    cuuint32_t est[4] = {1, 1, 1, 1};
+    if (int r = encode_map(&ma, a->src, 4, dims, str, box, est)) return r;
+  }
+  {
+    // packed weights [K rows][taps][w_pitch] read as ONE box {64 ch, TP taps, 8 rows}: tile row = k*TP + tap
+    cuuint64_t dims[3] = {(cuuint64_t)a->C, (cuuint64_t)p.taps, (cuuint64_t)a->w_rows};
+    cuuint64_t str[2] = {(cuuint64_t)a->w_pitch * 2, (cuuint64_t)p.taps * a->w_pitch * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)p.TP, 8};
+    cuuint32_t est[3] = {1, 1, 1};
+    if (int r = encode_map(&mw, a->w, 3, dims, str, box, est)) return r;
+  }
+  const size_t smem = ((p.w_bytes + 1023u) & ~1023u) + (size_t)SC_SLOTS * 128 * 128 + 1024 + 512;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.tiles < sms ? p.tiles : sms;
+  if (a->R == 4) return a->K == 1 ? launch_sc<4, 4, 1>(ma, mw, p, grid, smem, st) : launch_sc<4, 4, 8>(ma, mw, p, grid, smem, st);
+  return a->K == 1 ? launch_sc<5, 5, 1>(ma, mw, p, grid, smem, st) : launch_sc<5, 5, 8>(ma, mw, p, grid, smem, st);
+}
