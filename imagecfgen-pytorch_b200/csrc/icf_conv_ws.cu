@@ -34,6 +34,7 @@ constexpr int WS_THREADS = 32 * (1 + WS_ISSUERS + 4);
 constexpr int WS_MAX_CLASSES = 4, WS_MAX_TAPS = 25, WS_MAX_SUBS = 2, WS_MAX_ACC = 16, WS_MAX_SLOTS = 8;
 constexpr int WS_SMEM_BUDGET = 220 * 1024;
 constexpr int WS_MAX_GROUPS = 8;
+constexpr int WS_PROG_WORDS = 1536;                 // issuer schedules of all classes (4-byte actions), in the kernel parameters
 
 struct WsTap {
   int16_t dy;        // source row = i*sstep + dy
@@ -54,6 +55,7 @@ struct WsClass {
   int x0[WS_MAX_SUBS];         // TMA x start = j0*sstep + x0[sub]
   int tiles_x, cta_begin, cta_count;
   int ngroups;
+  int prog_off[WS_ISSUERS + 1];  // this class's issuer schedules inside WsParams::prog (contiguous, issuer after issuer)
   WsGroup grp[WS_MAX_GROUPS];
   WsTap taps[WS_MAX_TAPS];
 };
@@ -76,6 +78,11 @@ struct WsParams {
   void* dst;
   float* stats;                // [2][K] BatchNorm statistics of the stored values (+=), fused into the TMA-store epilogue
   int tma_store;               // 1: epilogue stages bf16 rows in shared memory and leaves through a TMA tensor store
+  // Issuer schedules, built on the host: which output rows a source row feeds, which of them an issuer owns, which
+  // open or complete an accumulator is the same for every column.  One 4-byte action per MMA chain:
+  //   bits 0-7 output row i | 8-12 first tap | 13-17 tap count | 18-19 kind (0 chain, 1 accumulator complete, 2 nothing)
+  //   | 20 chain opens the accumulator | 21 last action of this source row
+  uint32_t prog[WS_PROG_WORDS];
   unsigned long long* dbg;     // optional per-role cycle counters of CTA 0 (env ICF_WS_DEBUG), else NULL
   WsClass cls[WS_MAX_CLASSES];
 };
@@ -113,6 +120,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
   // barrier layout: slot_full[8] slot_empty[8] acc_full[16] acc_empty[16] w_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WS_MAX_SLOTS + 2 * WS_MAX_ACC + 1);
   float* sbias = reinterpret_cast<float*>(bars + 64);          // TILE_N floats, 512 B past the barriers
+  uint8_t* prog = reinterpret_cast<uint8_t*>(bars) + 1024;     // [tap table 256 B][this class's issuer schedules]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int cls = 0;
@@ -145,6 +153,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
+  // this class's tap table and issuer schedules -> shared memory, one word per thread (parameter space is read with
+  // independent loads here; the issue loop then pays one shared-memory load per action instead of indexed
+  // parameter loads and skipped groups, which cost ~1000 cycles per source row)
+  for (int t = (int)threadIdx.x; t < cl.ntaps; t += WS_THREADS)
+    sts64(smem_u32(prog) + 8u * t, cl.taps[t].a_off16, (uint32_t)(t * p.kchunks) * (((uint32_t)TILE_N * (uint32_t)p.rowb) >> 4));
+  for (int w = cl.prog_off[0] + (int)threadIdx.x; w < cl.prog_off[WS_ISSUERS]; w += WS_THREADS)
+    reinterpret_cast<uint32_t*>(prog + 256)[w - cl.prog_off[0]] = p.prog[w];
   if (warp == 1) tmem_alloc_rt(smem_u32(tmem_slot), p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -157,6 +172,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
   constexpr bool dbg_on = false;
 #endif
   long long w0 = 0, w1 = 0;                 // cycles spent in this role's two kinds of barrier waits
+  long long w2 = 0, w3 = 0, n_grp = 0;      // issuers: cycles in the MMA chains / in the commits, chains issued
   const long long t_begin = dbg_on ? clock64() : 0;
   const uint32_t W_BLOCK = (uint32_t)TILE_N * (uint32_t)p.rowb;      // one (tap, K chunk) block of the weight slab
 
@@ -193,71 +209,76 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     const uint32_t WB16 = W_BLOCK >> 4;
     const int wi = warp - 1;
     const uint32_t leader = elect_one();
+    const int Pi = cl.Pi, ylo = cl.ylo, yhi = cl.yhi;
+    const uint32_t tap_tab = smem_u32(prog), ent_tab = tap_tab + 256u + 4u * (uint32_t)(cl.prog_off[wi] - cl.prog_off[0]);
     mbar_wait(w_full, 0);
     tc_fence_after();
     const uint64_t d0 = make_desc_sw(0, 16, 8u * (uint32_t)p.rowb, p.rowb == 64 ? 4u : 2u);
     const uint32_t desc_hi = (uint32_t)(d0 >> 32), lbo_lo = (uint32_t)d0;     // low word without an address
     const uint32_t b_lo0 = ((slab_addr >> 4) & 0x3FFFu) | lbo_lo;
     const uint32_t kc16 = p.kc_bytes >> 4;
-    const int Pi = cl.Pi, ylo = cl.ylo, yhi = cl.yhi, dymax = cl.dymax, ngroups = cl.ngroups;
     const int amask = p.n_acc - 1;
     int s = 0;
     uint32_t ph = 0;
     int g_base = 0;                       // sequence number of this column's output row 0
     for (int col = r0; col < ncols; col += rstep) {
-      int next_done = 0;
+      uint32_t pc = ent_tab;
+      uint32_t nxt = lds32(pc);
       for (int y = ylo; y <= yhi; ++y) {
         WS_TIMED_WAIT(w0, slot_full(s), ph);
         tc_fence_after();
         const uint32_t a_lo0 = (((slots_addr + (uint32_t)s * p.slot_bytes) >> 4) & 0x3FFFu) | lbo_lo;
+        uint32_t flags;
 #pragma unroll 1                                   // keep the issue loop small: it has to live in the L0 instruction cache
-        for (int gi = 0; gi < ngroups; ++gi) {
-          const int dy = cl.grp[gi].dy;
-          const int num = y - dy;
-          const int i = p.sstep == 1 ? num : (num >> 1);
-          if (num < 0 || i >= Pi || (i & (WS_ISSUERS - 1)) != wi || (p.sstep == 2 && (num & 1))) continue;
-          const int g = g_base + i, acc = g & amask;
-          uint32_t accum = 1u;
-          if (y - cl.grp[gi].dprev < ylo) {          // first in-bounds contributor of output row i
-            WS_TIMED_WAIT(w1, acc_empty(acc), ((uint32_t)(g >> p.acc_shift) & 1u) ^ 1u);
-            tc_fence_after();
-            accum = 0u;
-          }
-          const uint32_t d_tmem = tmem_base + (uint32_t)acc * TILE_N;
-          const int t0 = cl.grp[gi].first, t1 = t0 + cl.grp[gi].count;
+        do {
+          const uint32_t e = nxt;
+          pc += 4;
+          nxt = lds32(pc);                         // every schedule ends with a spare word
+          flags = e >> 18;
+          const int g = g_base + (int)(e & 0xFFu), acc = g & amask;
+          if ((flags & 3u) == 0u) {
+            const long long t_mma = dbg_on ? clock64() : 0;
+            uint32_t accum = 1u;
+            if (flags & 4u) {
+              WS_TIMED_WAIT(w1, acc_empty(acc), ((uint32_t)(g >> p.acc_shift) & 1u) ^ 1u);
+              tc_fence_after();
+              accum = 0u;
+            }
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * TILE_N;
+            uint32_t tp = tap_tab + ((e >> 5) & 0xF8u);
+            const uint32_t tp_end = tp + ((e >> 10) & 0xF8u);
 #pragma unroll 1
-          for (int t = t0; t < t1; ++t) {
-            const uint32_t a_lo = a_lo0 + cl.taps[t].a_off16;
-            const uint32_t b_lo = b_lo0 + (uint32_t)(t * p.kchunks) * WB16;
-            if (KD > 0) {              // KD 16-wide K steps, chunk boundary every 4 (fully unrolled)
+            for (; tp < tp_end; tp += 8) {
+              const uint2 tt = lds64(tp);
+              const uint32_t a_lo = a_lo0 + tt.x, b_lo = b_lo0 + tt.y;
+              if (KD > 0) {              // KD 16-wide K steps, chunk boundary every 4 (fully unrolled)
 #pragma unroll
-              for (int k = 0; k < KD; ++k) {
-                umma_bf16_lo(d_tmem, a_lo + (k >> 2) * kc16 + 2 * (k & 3), b_lo + (k >> 2) * WB16 + 2 * (k & 3), desc_hi,
-                             idesc, accum, leader);
-                accum = 1u;
-              }
-            } else {
-              for (int kc = 0; kc < p.kchunks; ++kc) {
-                const int nk = (kc == p.kchunks - 1) ? p.kdepth_last : 4;
-                for (int k = 0; k < nk; ++k) {
-                  umma_bf16_lo(d_tmem, a_lo + kc * kc16 + 2 * k, b_lo + kc * WB16 + 2 * k, desc_hi, idesc, accum, leader);
+                for (int k = 0; k < KD; ++k) {
+                  umma_bf16_lo(d_tmem, a_lo + (k >> 2) * kc16 + 2 * (k & 3), b_lo + (k >> 2) * WB16 + 2 * (k & 3), desc_hi,
+                               idesc, accum, leader);
                   accum = 1u;
+                }
+              } else {
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                  const int nk = (kc == p.kchunks - 1) ? p.kdepth_last : 4;
+                  for (int k = 0; k < nk; ++k) {
+                    umma_bf16_lo(d_tmem, a_lo + kc * kc16 + 2 * k, b_lo + kc * WB16 + 2 * k, desc_hi, idesc, accum, leader);
+                    accum = 1u;
+                  }
                 }
               }
             }
+            if (dbg_on) { w2 += clock64() - t_mma; ++n_grp; }
+          } else if ((flags & 3u) == 1u) {
+            umma_commit_if(acc_full(acc), leader);      // every MMA into this accumulator has been issued (by this thread)
           }
-        }
+        } while (!(flags & 8u));
         umma_commit_if(slot_empty(s), leader);       // arrives once this issuer's MMAs on the slot have retired
         if (++s == p.n_slots) { s = 0; ph ^= 1; }
-        while (next_done < Pi && (next_done * p.sstep + dymax <= y || y == yhi)) {
-          if ((next_done & (WS_ISSUERS - 1)) == wi)
-            umma_commit_if(acc_full((g_base + next_done) & amask), leader);   // every row has an in-bounds source row
-          ++next_done;
-        }
       }
       g_base += Pi;
     }
-    if (dbg_on && lane == 0 && wi == 0) { p.dbg[2] = clock64() - t_begin; p.dbg[3] = w0; p.dbg[4] = w1; }
+    if (dbg_on && lane == 0 && wi == 0) { p.dbg[2] = clock64() - t_begin; p.dbg[3] = w0; p.dbg[4] = w1; p.dbg[8] = w2; p.dbg[9] = w3; p.dbg[10] = n_grp; }
   } else {
     // ===== epilogue: TMEM lane m = x_local*NG + n_local =====
     const int q4 = warp & 3;
@@ -561,8 +582,6 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   q.slab_bytes = ((uint32_t)(max_ntaps * q.kchunks * tile_n) * (uint32_t)q.rowb + 1023u) & ~1023u;
   const int64_t stage_bytes = 2 * 128 * tile_n * 2;
   if ((int64_t)q.slab_bytes + stage_bytes + 2 * (int64_t)q.slot_bytes > WS_SMEM_BUDGET) return -1;
-  q.n_slots = (int)((WS_SMEM_BUDGET - (int64_t)q.slab_bytes - stage_bytes) / q.slot_bytes);
-  if (q.n_slots > WS_MAX_SLOTS) q.n_slots = WS_MAX_SLOTS;
   q.tiles_n = icf::cdiv(a->N, q.NG);
 
   // ---- tap tables, CTA partition over (class, k-tile) ----
@@ -598,6 +617,49 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
     work[c] = (double)cl.tiles_x * cl.Pi * cl.ntaps;
     total += work[c];
   }
+  // ---- issuer schedules (see WsParams::prog) ----
+  int64_t prog_bytes = 0;                            // shared memory: tap table + the longest class's issuer schedules
+  {
+    int used = 0;
+    for (int c = 0; c < q.n_classes; ++c) {
+      WsClass& cl = q.cls[c];
+      if (cl.Pi > 256) return -1;
+      for (int wi = 0; wi < WS_ISSUERS; ++wi) {
+        cl.prog_off[wi] = used;
+        for (int y = cl.ylo; y <= cl.yhi; ++y) {
+          const int row_begin = used;
+          for (int gi = 0; gi < cl.ngroups; ++gi) {
+            const int num = y - cl.grp[gi].dy;
+            const int i = q.sstep == 1 ? num : (num >> 1);
+            if (num < 0 || i >= cl.Pi || (i & (WS_ISSUERS - 1)) != wi || (q.sstep == 2 && (num & 1))) continue;
+            const bool opens = y - cl.grp[gi].dprev < cl.ylo;     // first in-bounds contributor of output row i
+            if (used >= WS_PROG_WORDS - 2) return -1;
+            q.prog[used++] = (uint32_t)i | ((uint32_t)cl.grp[gi].first << 8) | ((uint32_t)cl.grp[gi].count << 13) | (opens ? 1u << 20 : 0u);
+          }
+          for (int i = wi; i < cl.Pi; i += WS_ISSUERS) {           // output rows whose last source row is y
+            int yc = i * q.sstep + cl.dymax;
+            yc = yc < cl.ylo ? cl.ylo : (yc > cl.yhi ? cl.yhi : yc);
+            if (yc != y) continue;
+            if (used >= WS_PROG_WORDS - 2) return -1;
+            q.prog[used++] = (uint32_t)i | (1u << 18);
+          }
+          if (used == row_begin) {
+            if (used >= WS_PROG_WORDS - 2) return -1;
+            q.prog[used++] = 2u << 18;
+          }
+          q.prog[used - 1] |= 1u << 21;
+        }
+        q.prog[used++] = 2u << 18;                                // spare word: the issue loop reads one action ahead
+      }
+      cl.prog_off[WS_ISSUERS] = used;
+      const int64_t need = 256 + 4 * (int64_t)(used - cl.prog_off[0]);
+      prog_bytes = need > prog_bytes ? need : prog_bytes;
+    }
+    prog_bytes = (prog_bytes + 255) & ~(int64_t)255;
+  }
+  if ((int64_t)q.slab_bytes + stage_bytes + prog_bytes + 2 * (int64_t)q.slot_bytes > WS_SMEM_BUDGET) return -1;
+  q.n_slots = (int)((WS_SMEM_BUDGET - (int64_t)q.slab_bytes - stage_bytes - prog_bytes) / q.slot_bytes);
+  if (q.n_slots > WS_MAX_SLOTS) q.n_slots = WS_MAX_SLOTS;
   const int budget = sm_count();
   int grid = 0;
   for (int c = 0; c < q.n_classes; ++c) {
@@ -615,7 +677,7 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   static unsigned long long* dbg_buf = []() -> unsigned long long* {
     const char* e = getenv("ICF_WS_DEBUG");
     void* d = nullptr;
-    if (e && e[0] && e[0] != '0' && cudaMalloc(&d, 64) == cudaSuccess) cudaMemset(d, 0, 64);
+    if (e && e[0] && e[0] != '0' && cudaMalloc(&d, 128) == cudaSuccess) cudaMemset(d, 0, 128);
     return reinterpret_cast<unsigned long long*>(d);
   }();
   q.dbg = dbg_buf;
@@ -656,7 +718,8 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
     if (int r = encode_map_swz(&mb, a->w, 2, dims, str, box, est, q.rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B)) return r;
   }
   // shared memory: always more than half an SM's worth so that exactly one CTA (and one TMEM allocation) is resident
-  size_t smem = (size_t)q.slab_bytes + (size_t)q.n_slots * q.slot_bytes + (size_t)stage_bytes + 1024 + 1024;
+  size_t smem = (size_t)q.slab_bytes + (size_t)q.n_slots * q.slot_bytes + (size_t)stage_bytes + 1024 + 1024 + (size_t)prog_bytes;
+
   if (smem < 120 * 1024) smem = 120 * 1024;
   int r;
   const int kd = q.kchunks <= 2 ? 4 * (q.kchunks - 1) + q.kdepth_last : 0;
@@ -681,14 +744,14 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   if (r) return r;
   const bool stats_fused = q.stats != nullptr;
   if (q.dbg) {
-    unsigned long long h[8];
+    unsigned long long h[16];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, q.dbg, sizeof(h), cudaMemcpyDeviceToHost);
     fprintf(stderr,
             "[icf ws] K=%d C=%d R=%d stride=%d form=%d tile_n=%d XG=%d NG=%d slots=%d slot=%uB slab=%uB grid=%d | CTA0 cycles: "
-            "producer %llu (wait empty %llu) | mma %llu (wait full %llu, wait acc %llu) | epilogue %llu (wait acc_full %llu, tmem ld %llu)\n",
+            "producer %llu (wait empty %llu) | mma %llu (wait full %llu, wait acc %llu, chains %llu in %llu, commits %llu) | epilogue %llu (wait acc_full %llu, tmem ld %llu)\n",
             a->K, a->C, a->R, a->stride, a->form, tile_n, q.XG, q.NG, q.n_slots, q.slot_bytes, q.slab_bytes, grid, h[0], h[1],
-            h[2], h[3], h[4], h[5], h[6], h[7]);
+            h[2], h[3], h[4], h[10], h[8], h[9], h[5], h[6], h[7]);
   }
   if (a->stats && !stats_fused) {
     if (a->out_f32) { icf::set_error("row-streaming conv: BatchNorm statistics need a bf16 destination"); return 1; }
