@@ -416,7 +416,12 @@ __device__ __forceinline__ V8 cvt8(const uint4& u) {          // 8 packed bf16 -
 __device__ __forceinline__ uint4 ldraw8(const void* base, int64_t idx) {
   return __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx));
 }
-constexpr int VU = 4;            // pixels in flight per thread in the bf16 streaming loops (memory-level parallelism)
+// VU (template parameter of the streaming kernels): pixels in flight per thread in the bf16 loops (memory-level
+// parallelism); tuning aids ICF_EW_VU (2, 4, 8) and ICF_EW_CAP (blocks per SM of the grid)
+inline int env_int(const char* name) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+}
 
 __device__ __forceinline__ void st8(void* base, int dtype, int64_t idx, const V8& r) {
   if (dtype == ICF_F32) {
@@ -443,10 +448,38 @@ __device__ __forceinline__ V8 ldf8(const float* p) {   // 8 consecutive floats, 
 constexpr int VT = 256;          // threads per block of the vector kernels
 constexpr int VSM = 2048;        // channels a block can hold partial sums for
 
-// flush per-thread channel partials: shared-memory atomics, then one global atomic per channel per block
+// flush per-thread channel partials, then one global atomic per channel per block.  Up to 256 channels per block
+// (the layers of the step): lanes that share a channel group combine through shuffles, each warp stores its row, the
+// rows are summed — no shared-memory atomics (float atomics on shared memory are compare-and-swap loops; 64 threads
+// on one address cost tens of microseconds per block).  Wider blocks keep the atomic path (<= 4 threads per address).
 template <int NS>
 __device__ __forceinline__ void flush_partials(float (*acc)[8], int cbase_block, int c0, int C, int span,
                                                float* const* dst, float* sm) {
+  const int gpb = span >> 3;
+  if (gpb <= 32 && (gpb & (gpb - 1)) == 0 && blockDim.x == VT) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = gpb; o < 32; o <<= 1) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[s][j] += __shfl_xor_sync(0xffffffffu, acc[s][j], o);
+    }
+    if (lane < gpb) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm[(warp * NS + s) * span + lane * 8 + j] = acc[s][j];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NS * span; i += VT) {
+      const int s = i / span, cc = i - s * span, c = cbase_block + cc;
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < VT / 32; ++w) t += sm[(w * NS + s) * span + cc];
+      if (c < C && dst[s]) atomicAdd(dst[s] + c, t);
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < NS * span; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
   if (c0 < C) {
@@ -497,18 +530,21 @@ __device__ __forceinline__ const V8& cached_mask(MaskCache& mc, const float* mas
   return mc.v;
 }
 
-inline int vgrid(int C, int64_t pixels) {
+inline int vgrid(int C, int64_t pixels, int per_sm = 8) {
+  static const int cap_env = env_int("ICF_EW_CAP");
+  if (cap_env > 0) per_sm = cap_env;
   const int cg = C >> 3;
   const int gpb = cg < VT ? cg : VT;
   const int cblocks = (cg + gpb - 1) / gpb;
   const int rows = VT / gpb;
   int64_t pblocks = (pixels + rows - 1) / rows;
-  const int64_t cap = (148 * 8 + cblocks - 1) / cblocks;
+  const int64_t cap = (148 * per_sm + cblocks - 1) / cblocks;
   if (pblocks > cap) pblocks = cap;
   if (pblocks < 1) pblocks = 1;
   return (int)(pblocks * cblocks);
 }
 
+template <int VU>
 __global__ void __launch_bounds__(VT) scale_shift_mask_v8(const void* y, int ydt, int ypitch, void* u, int udt, int upitch,
                                                           int64_t pixels, int pps, int C, const float* scale,
                                                           const float* shift, const float* mask, int mpitch) {
@@ -518,8 +554,7 @@ __global__ void __launch_bounds__(VT) scale_shift_mask_v8(const void* y, int ydt
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc.v[j] = scale ? scale[m.c0 + j] : 1.f; sh.v[j] = (scale && shift) ? shift[m.c0 + j] : 0.f; }
   MaskCache mc;
-  for (int64_t pix = m.pix0; pix < m.pix_end; pix += m.pstride) {
-    V8 v = ld8(y, ydt, pix * ypitch + m.c0);
+  auto process = [&](int64_t pix, V8 v) {
     if (scale) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v.v[j] = fmaf(v.v[j], sc.v[j], sh.v[j]);
@@ -530,10 +565,28 @@ __global__ void __launch_bounds__(VT) scale_shift_mask_v8(const void* y, int ydt
       for (int j = 0; j < 8; ++j) v.v[j] *= mk.v[j];
     }
     st8(u, udt, pix * upitch + m.c0, v);
+  };
+  if (ydt == ICF_BF16) {
+    for (int64_t pix = m.pix0; pix < m.pix_end; pix += VU * m.pstride) {
+      uint4 yr[VU];
+#pragma unroll
+      for (int k = 0; k < VU; ++k) {
+        const int64_t pu = pix + k * m.pstride;
+        if (pu < m.pix_end) yr[k] = ldraw8(y, pu * ypitch + m.c0);
+      }
+#pragma unroll
+      for (int k = 0; k < VU; ++k) {
+        const int64_t pu = pix + k * m.pstride;
+        if (pu < m.pix_end) process(pu, cvt8(yr[k]));
+      }
+    }
+  } else {
+    for (int64_t pix = m.pix0; pix < m.pix_end; pix += m.pstride) process(pix, ld8(y, ydt, pix * ypitch + m.c0));
   }
 }
 
-__global__ void __launch_bounds__(VT, 3) bn_bwd_reduce_v8(const void* dU, int ddt, int dpitch, const void* y, int ydt, int ypitch,
+template <int VU>
+__global__ void __launch_bounds__(VT, VU > 4 ? 2 : 3) bn_bwd_reduce_v8(const void* dU, int ddt, int dpitch, const void* y, int ydt, int ypitch,
                                                        int64_t pixels, int pps, int C, const float* mask, int mpitch,
                                                        const float* mean, const float* invstd, float* sums) {
   __shared__ float sm[2 * VSM];
@@ -601,6 +654,7 @@ __global__ void __launch_bounds__(VT) col_stats_v8(const void* y, int ydt, int y
   flush_partials<2>(acc, m.cbase_block, m.c0, C, m.span, dst, sm);
 }
 
+template <int VU>
 __global__ void __launch_bounds__(VT, 2) act_backward_v8(const icf_actbwd_args a) {
   __shared__ float sm[VSM];
   const VMap m = vmap(a.C, a.pixels);
@@ -684,6 +738,10 @@ __global__ void __launch_bounds__(VT, 2) act_backward_v8(const icf_actbwd_args a
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline int vu_choice() {
+  static const int v = env_int("ICF_EW_VU");
+  return v;
+}
 
 }  // namespace
 
@@ -987,8 +1045,11 @@ int icf_scale_shift_mask(const void* y, int32_t y_dtype, int32_t y_pitch, void* 
   if (pixels == 0) return 0;
   if ((C & 7) == 0 && (y_pitch & 7) == 0 && (u_pitch & 7) == 0 && al16(y) && al16(u) && (!mask || ((mask_pitch & 3) == 0 && al16(mask))) &&
       (!scale || al16(scale)) && (!shift || al16(shift))) {
-    scale_shift_mask_v8<<<vgrid(C, pixels), VT, 0, icf::as_stream(stream)>>>(y, y_dtype, y_pitch, u, u_dtype, u_pitch, pixels,
-                                                                             pixels_per_sample, C, scale, shift, mask, mask_pitch);
+#define ICF_SSM(V) scale_shift_mask_v8<V><<<vgrid(C, pixels, 3), VT, 0, icf::as_stream(stream)>>>(y, y_dtype, y_pitch, u, u_dtype, u_pitch, \
+                                                          pixels, pixels_per_sample, C, scale, shift, mask, mask_pitch)
+    const int vu = vu_choice();
+    if (vu == 2) ICF_SSM(2); else if (vu == 8) ICF_SSM(8); else ICF_SSM(4);
+#undef ICF_SSM
     return icf::check_launch("scale_shift_mask_v8");
   }
   scale_shift_mask_kernel<<<ew_grid(pixels * C, 4), EW_THREADS, 0, icf::as_stream(stream)>>>(
@@ -1004,9 +1065,11 @@ int icf_bn_bwd_reduce(const void* dU, int32_t d_dtype, int32_t d_pitch, const vo
   if (pixels == 0) return 0;
   if ((C & 7) == 0 && (d_pitch & 7) == 0 && (y_pitch & 7) == 0 && al16(dU) && al16(y) && al16(save_mean) && al16(save_invstd) &&
       (!mask || ((mask_pitch & 3) == 0 && al16(mask)))) {
-    bn_bwd_reduce_v8<<<vgrid(C, pixels), VT, 0, icf::as_stream(stream)>>>(dU, d_dtype, d_pitch, y, y_dtype, y_pitch, pixels,
-                                                                          pixels_per_sample, C, mask, mask_pitch, save_mean,
-                                                                          save_invstd, sums);
+#define ICF_BBR(V, PER_SM) bn_bwd_reduce_v8<V><<<vgrid(C, pixels, PER_SM), VT, 0, icf::as_stream(stream)>>>(                 \
+      dU, d_dtype, d_pitch, y, y_dtype, y_pitch, pixels, pixels_per_sample, C, mask, mask_pitch, save_mean, save_invstd, sums)
+    const int vu = vu_choice();            // one resident wave: measured best (profiles/r01_ew_bench.log)
+    if (vu == 2) ICF_BBR(2, 3); else if (vu == 8) ICF_BBR(8, 2); else ICF_BBR(4, 3);
+#undef ICF_BBR
     return icf::check_launch("bn_bwd_reduce_v8");
   }
   const int groups = icf::cdiv(C, 32);
@@ -1030,7 +1093,10 @@ int icf_act_backward(const icf_actbwd_args* a, void* stream) {
     if (a->bn_sums) ok = ok && al16(a->bn_sums) && al16(a->bn_gamma) && al16(a->bn_mean) && al16(a->bn_invstd) && (a->C & 3) == 0 &&
                       (!a->bn_mask || ((a->bn_mask_pitch & 3) == 0 && al16(a->bn_mask)));
     if (ok) {
-      act_backward_v8<<<vgrid(a->C, a->pixels), VT, 0, icf::as_stream(stream)>>>(*a);
+      const int vu = vu_choice();
+      if (vu == 2) act_backward_v8<2><<<vgrid(a->C, a->pixels, 2), VT, 0, icf::as_stream(stream)>>>(*a);
+      else if (vu == 8) act_backward_v8<8><<<vgrid(a->C, a->pixels, 2), VT, 0, icf::as_stream(stream)>>>(*a);
+      else act_backward_v8<4><<<vgrid(a->C, a->pixels, 2), VT, 0, icf::as_stream(stream)>>>(*a);
       return icf::check_launch("act_backward_v8");
     }
   }
