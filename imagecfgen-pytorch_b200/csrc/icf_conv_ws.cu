@@ -29,8 +29,11 @@ namespace {
 
 using namespace icf_tc;
 
-constexpr int WS_ISSUERS = 4;                       // MMA-issuing warps: output row i belongs to issuer i % WS_ISSUERS
-constexpr int WS_THREADS = 32 * (1 + WS_ISSUERS + 4);
+constexpr int WS_ISSUERS = 3;                       // MMA-issuing warps: output row i belongs to issuer i % WS_ISSUERS
+// (12 warps = 3 per SM sub-partition, which leaves 168 registers per thread; a 13th warp would cap it at 128)
+constexpr int WS_EPI_GROUPS = 2;                    // epilogue warpgroups (4 warps each): output row g belongs to group g % 2
+constexpr int WS_EPI0 = 32 * (1 + WS_ISSUERS);      // first epilogue thread
+constexpr int WS_THREADS = WS_EPI0 + 128 * WS_EPI_GROUPS;
 constexpr int WS_MAX_CLASSES = 4, WS_MAX_TAPS = 25, WS_MAX_SUBS = 2, WS_MAX_ACC = 16, WS_MAX_SLOTS = 8;
 constexpr int WS_SMEM_BUDGET = 220 * 1024;
 constexpr int WS_MAX_GROUPS = 8;
@@ -105,6 +108,11 @@ struct WsParams {
 #else
 #define WS_TIMED_WAIT(counter, bar, par) mbar_wait(bar, par)
 #endif
+
+__device__ __forceinline__ void epi_bar(int grp) {   // named barrier of one epilogue warpgroup (ids 1, 2)
+  if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
 
 template <int TILE_N, int KD>
 __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_constant__ CUtensorMap map_a,
@@ -286,12 +294,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
     const int x_local = m >> p.ng_shift, n_local = m & (p.NG - 1);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
     // bias tile -> shared memory (zero where absent / beyond K), visible to the four epilogue warps
-    for (int j = (int)threadIdx.x - 32 * (1 + WS_ISSUERS); j < TILE_N; j += 128) sbias[j] = (p.bias && k0 + j < p.K) ? __ldg(p.bias + k0 + j) : 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // Two epilogue warpgroups alternate output rows: a single warp per SM sub-partition pays every instruction and
+    // barrier at full latency (~1200 cycles per 128x32 row measured), two rows in flight hide half of it.  Each
+    // group owns one staging buffer and one named barrier.
+    const int grp = ((int)threadIdx.x - WS_EPI0) >> 7;
+    for (int j = (int)threadIdx.x - WS_EPI0; j < TILE_N; j += 128 * WS_EPI_GROUPS) sbias[j] = (p.bias && k0 + j < p.K) ? __ldg(p.bias + k0 + j) : 0.f;
+    asm volatile("bar.sync 3, %0;" ::"n"(128 * WS_EPI_GROUPS) : "memory");
     const int esize = p.out_f32 ? 4 : 2;
     // fused BatchNorm statistics: thread -> one 8-channel chunk (et % CH) of the staged tile and every (128/CH)-th row
     constexpr int CH = TILE_N / 8;
-    const int et = (int)threadIdx.x - 32 * (1 + WS_ISSUERS);
+    const int et = ((int)threadIdx.x - WS_EPI0) & 127;
     const int st_ch = et % CH, st_r0 = et / CH;
     float st_sum[8], st_sq[8];
 #pragma unroll
@@ -315,14 +327,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         constexpr uint32_t ROW_B = TILE_N * 2, BUF_B = 128 * ROW_B;
         const uint32_t sw = TILE_N == 64 ? (uint32_t)(m & 7) : (TILE_N == 32 ? (uint32_t)((m >> 1) & 3) : (uint32_t)((m >> 2) & 1));
         const uint32_t srow = smem_u32(stage) + (uint32_t)m * ROW_B;
-        const bool issuer = (int)threadIdx.x == 32 * (1 + WS_ISSUERS);
+        const bool issuer = et == 0;
         const int ox = cl.px + jt * p.XG * p.ostep, n0 = nt * p.NG;
+        const uint32_t buf = (uint32_t)grp * BUF_B;
         for (int i = 0; i < cl.Pi; ++i, ++g) {
+          if ((g & (WS_EPI_GROUPS - 1)) != grp) continue;
           const int acc = g & (p.n_acc - 1);
+          if (issuer) bulk_wait_read<0>();          // this group's previous store has drained the staging buffer
           WS_TIMED_WAIT(w0, acc_full(acc), (uint32_t)(g >> p.acc_shift) & 1u);
           tc_fence_after();
+          epi_bar(grp);                             // buffer free (and the statistics pass over it finished)
           const long long t_ld = dbg_on ? clock64() : 0;
-          uint4 outv[TILE_N / 8];
 #pragma unroll
           for (int c0 = 0; c0 < TILE_N; c0 += 32) {
             uint32_t va[16], vb[16];
@@ -336,20 +351,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
               if (lane == 0) mbar_arrive(acc_empty(acc));
             }
             const int nv = p.K - (k0 + c0);
+            uint4 o0, o1, o2, o3;
             epi16_pack(va, sbias + c0, *reinterpret_cast<const float(*)[16]>(&mk[c0]), p.act, p.slope,
-                       nv < 0 ? 0 : (nv < 16 ? nv : 16), outv[c0 / 8], outv[c0 / 8 + 1]);
-            if (TILE_N > 16)
+                       nv < 0 ? 0 : (nv < 16 ? nv : 16), o0, o1);
+            sts128(srow + buf + (((uint32_t)(c0 / 8) ^ sw) << 4), o0);
+            sts128(srow + buf + (((uint32_t)(c0 / 8 + 1) ^ sw) << 4), o1);
+            if (TILE_N > 16) {
               epi16_pack(vb, sbias + c0 + 16, *reinterpret_cast<const float(*)[16]>(&mk[TILE_N > 16 ? c0 + 16 : 0]), p.act,
-                         p.slope, nv < 16 ? 0 : (nv < 32 ? nv - 16 : 16), outv[TILE_N > 16 ? c0 / 8 + 2 : 0],
-                         outv[TILE_N > 16 ? c0 / 8 + 3 : 1]);
+                         p.slope, nv < 16 ? 0 : (nv < 32 ? nv - 16 : 16), o2, o3);
+              sts128(srow + buf + (((uint32_t)(c0 / 8 + 2) ^ sw) << 4), o2);
+              sts128(srow + buf + (((uint32_t)(c0 / 8 + 3) ^ sw) << 4), o3);
+            }
           }
-          const uint32_t buf = (uint32_t)(g & 1) * BUF_B;
-          if (issuer) bulk_wait_read<1>();          // the store that last read this buffer has drained it
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-          for (int c = 0; c < TILE_N / 8; ++c) sts128(srow + buf + (((uint32_t)c ^ sw) << 4), outv[c]);
           fence_proxy_async();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          epi_bar(grp);
           if (issuer) {
             tma_store_4d(&map_o, smem_u32(stage) + buf, k0, n0, ox, cl.py + i * p.ostep);
             bulk_commit();
@@ -384,6 +399,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
                       ((((int64_t)(valid ? n : 0) * p.P + cl.py) * p.Q + cl.px + (int64_t)(valid ? jj : 0) * p.ostep) * p.out_pitch + k0) * esize;
       const int64_t row_step = (int64_t)p.ostep * p.Q * p.out_pitch * esize;
       for (int i = 0; i < cl.Pi; ++i, ++g, orow += row_step) {
+        if ((g & (WS_EPI_GROUPS - 1)) != grp) continue;
         const int acc = g & (p.n_acc - 1);
         WS_TIMED_WAIT(w0, acc_full(acc), (uint32_t)(g >> p.acc_shift) & 1u);
         tc_fence_after();
@@ -420,7 +436,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         }
       }
     }
-    if (p.tma_store && (int)threadIdx.x == 32 * (1 + WS_ISSUERS)) bulk_wait_all();
+    if (p.tma_store && et == 0) bulk_wait_all();
     if (p.tma_store && p.stats) {
       // lanes that share a chunk (same et % CH) first combine through shuffles, then one atomic per channel and warp
 #pragma unroll
@@ -442,7 +458,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         }
       }
     }
-    if (dbg_on && threadIdx.x == 32 * (1 + WS_ISSUERS)) { p.dbg[5] = clock64() - t_begin; p.dbg[6] = w0; p.dbg[7] = w1; }
+    if (dbg_on && threadIdx.x == WS_EPI0) { p.dbg[5] = clock64() - t_begin; p.dbg[6] = w0; p.dbg[7] = w1; }
   }
   tc_fence_before();
   __syncthreads();
@@ -631,7 +647,7 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
           for (int gi = 0; gi < cl.ngroups; ++gi) {
             const int num = y - cl.grp[gi].dy;
             const int i = q.sstep == 1 ? num : (num >> 1);
-            if (num < 0 || i >= cl.Pi || (i & (WS_ISSUERS - 1)) != wi || (q.sstep == 2 && (num & 1))) continue;
+            if (num < 0 || i >= cl.Pi || i % WS_ISSUERS != wi || (q.sstep == 2 && (num & 1))) continue;
             const bool opens = y - cl.grp[gi].dprev < cl.ylo;     // first in-bounds contributor of output row i
             if (used >= WS_PROG_WORDS - 2) return -1;
             q.prog[used++] = (uint32_t)i | ((uint32_t)cl.grp[gi].first << 8) | ((uint32_t)cl.grp[gi].count << 13) | (opens ? 1u << 20 : 0u);
