@@ -203,8 +203,10 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
 // Both operands are [pixels][channels] tensors, i.e. MN-major for the MMA (the reduction runs over pixels).
 // A K-block is a BOX (bn images x bp rows x bq columns, bn*bp*bq in {16,32,48,64}) of the small tensor's pixel
 // grid, over-covering it where needed: out-of-range pixels of `small` are zero-filled by TMA, which also
-// cancels whatever the matching `big` box holds there.  One CTA owns one (a-tile, b-tile, tap) and a strided
-// subset of the K-blocks, accumulates in TMEM and adds its partial tile into dw with fp32 atomics.
+// cancels whatever the matching `big` box holds there.  One CTA owns one (a-tile, b-tile, group of `tp` taps) and a
+// strided subset of the K-blocks: the `small` box of a K-block is loaded ONCE and multiplied with the `big` boxes of
+// all taps of the group (one TMEM accumulator per tap), so `small` is re-read taps/tp times instead of once per tap
+// (the per-tap version was bound by L2->SM traffic).  Partial tiles are added into dw with fp32 vector reductions.
 // ------------------------------------------------------------------------------------------------
 struct WgParams {
   int N, P, Q, A;          // small: [N][P][Q][a_pitch]
@@ -214,17 +216,20 @@ struct WgParams {
   int blocks_q, blocks_p, blocks_n;
   int a_tiles, b_tiles;
   uint32_t rows;           // bq*bp*bn
+  int tp, tap_groups;      // taps per CTA, ceil(taps / tp)
+  int stages;
+  uint32_t stage_bytes, tmem_cols;
   float* dw;
 };
 
-template <int TILE_N, int STAGES>
+template <int TILE_N>
 __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_s,
                                                                const __grid_constant__ CUtensorMap map_g,
                                                                const __grid_constant__ WgParams p) {
   constexpr uint32_t CHUNK_BYTES = 64 * 64 * 2;                  // one 64-channel x 64-pixel chunk (max rows)
-  constexpr int NB = TILE_N / 64;                                // B chunks
-  constexpr uint32_t STAGE_BYTES = (2 + NB) * CHUNK_BYTES;
-  constexpr int TMEM_COLS = TILE_N < 32 ? 32 : TILE_N;
+  constexpr int NB = TILE_N / 64;                                // B chunks per tap
+  const uint32_t STAGE_BYTES = p.stage_bytes;                    // [small chunk 0][small chunk 1][tp x NB big chunks]
+  const int STAGES = p.stages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -232,10 +237,11 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   int t = blockIdx.x;
-  const int tap = t % p.taps; t /= p.taps;
+  const int tg = t % p.tap_groups; t /= p.tap_groups;
   const int bt = t % p.b_tiles;
   const int at = t / p.b_tiles;
-  const int r = tap / p.S, s = tap - r * p.S;
+  const int tap0 = tg * p.tp;
+  const int ntap = p.taps - tap0 < p.tp ? p.taps - tap0 : p.tp;
   const int a0 = at * BLOCK_M, b0 = bt * TILE_N;
   const int n_blocks = p.blocks_q * p.blocks_p * p.blocks_n;
   const int split = blockIdx.y, splits = gridDim.y;
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+  if (warp == 1) tmem_alloc_rt(smem_u32(tmem_slot), p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -264,38 +270,48 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < my_blocks; ++i) {
         int blk = split + i * splits;
         const int qb = blk % p.blocks_q; blk /= p.blocks_q;
         const int pb = blk % p.blocks_p;
         const int nb = blk / p.blocks_p;
         const int q0 = qb * p.bq, p0 = pb * p.bp, n0 = nb * p.bn;
-        const int st = i % STAGES;
-        mbar_wait(empty_bar(st), ((i / STAGES) & 1) ^ 1);
-        const uint32_t base = smem_u32(smem + st * STAGE_BYTES);
-        mbar_expect_tx(full_bar(st), chunk_bytes * (2 + NB));
+        mbar_wait(empty_bar(st), ph ^ 1);
+        const uint32_t base = smem_u32(smem) + (uint32_t)st * STAGE_BYTES;
+        mbar_expect_tx(full_bar(st), chunk_bytes * (uint32_t)(2 + ntap * NB));
         tma_load_4d(base, &map_s, full_bar(st), a0, q0, p0, n0);
         tma_load_4d(base + CHUNK_BYTES, &map_s, full_bar(st), a0 + 64, q0, p0, n0);
-        const int x = q0 * p.stride - p.pad + s, y = p0 * p.stride - p.pad + r;
+        for (int tt = 0; tt < ntap; ++tt) {
+          const int tap = tap0 + tt, r = tap / p.S, s = tap - r * p.S;
+          const int x = q0 * p.stride - p.pad + s, y = p0 * p.stride - p.pad + r;
 #pragma unroll
-        for (int j = 0; j < NB; ++j)
-          tma_load_4d(base + (2 + j) * CHUNK_BYTES, &map_g, full_bar(st), b0 + 64 * j, x, y, n0);
+          for (int j = 0; j < NB; ++j)
+            tma_load_4d(base + (uint32_t)(2 + tt * NB + j) * CHUNK_BYTES, &map_g, full_bar(st), b0 + 64 * j, x, y, n0);
+        }
+        if (++st == STAGES) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BLOCK_M, TILE_N, 1, 1);
       const int ksteps = (int)p.rows / UMMA_K;
+      int st = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < my_blocks; ++i) {
-        const int st = i % STAGES;
-        mbar_wait(full_bar(st), (i / STAGES) & 1);
+        mbar_wait(full_bar(st), ph);
         tc_fence_after();
-        const uint32_t base = smem_u32(smem + st * STAGE_BYTES);
+        const uint32_t base = smem_u32(smem) + (uint32_t)st * STAGE_BYTES;
         // MN-major, 128B swizzle: 64-channel chunks CHUNK_BYTES apart (LBO), 8-pixel groups 1024 B apart (SBO)
-        const uint64_t adesc = make_desc(base, CHUNK_BYTES, 1024), bdesc = make_desc(base + 2 * CHUNK_BYTES, CHUNK_BYTES, 1024);
-        for (int k = 0; k < ksteps; ++k)   // 16 pixels = 2048 B = 128 descriptor units per step
-          umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (i | k) ? 1u : 0u);
+        const uint64_t adesc = make_desc(base, CHUNK_BYTES, 1024);
+        for (int tt = 0; tt < ntap; ++tt) {
+          const uint64_t bdesc = make_desc(base + (uint32_t)(2 + tt * NB) * CHUNK_BYTES, CHUNK_BYTES, 1024);
+          for (int k = 0; k < ksteps; ++k)   // 16 pixels = 2048 B = 128 descriptor units per step
+            umma_bf16(tmem_base + (uint32_t)(tt * TILE_N), adesc + 128 * k, bdesc + 128 * k, idesc, (i | k) ? 1u : 0u);
+        }
         umma_commit(empty_bar(st));
+        if (++st == STAGES) { st = 0; ph ^= 1; }
       }
       if (my_blocks > 0) umma_commit(tmem_full_bar);
       else mbar_arrive(tmem_full_bar);
@@ -307,24 +323,27 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
     tc_fence_after();
     if (my_blocks > 0) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < TILE_N; c0 += 16) {
-        if (b0 + c0 >= p.B) break;
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (a < p.A) {
-          float* o = p.dw + ((int64_t)a * p.taps + tap) * p.B + b0 + c0;
-          if (b0 + c0 + 16 <= p.B && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-            // four 16-byte vector reductions instead of sixteen scalar atomics (the split-K epilogue is L2-atomic bound)
+      for (int tt = 0; tt < ntap; ++tt) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < TILE_N; c0 += 16) {
+          if (b0 + c0 >= p.B) break;
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(tt * TILE_N + c0), v);
+          tmem_ld_wait();
+          if (a < p.A) {
+            float* o = p.dw + ((int64_t)a * p.taps + tap0 + tt) * p.B + b0 + c0;
+            if (b0 + c0 + 16 <= p.B && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+              // four 16-byte vector reductions instead of sixteen scalar atomics (the split-K epilogue is L2-atomic bound)
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(__uint_as_float(v[j])),
-                           "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
-                           : "memory");
-          } else {
+              for (int j = 0; j < 16; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(__uint_as_float(v[j])),
+                             "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                             : "memory");
+            } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (b0 + c0 + j < p.B) atomicAdd(o + j, __uint_as_float(v[j]));
+              for (int j = 0; j < 16; ++j)
+                if (b0 + c0 + j < p.B) atomicAdd(o + j, __uint_as_float(v[j]));
+            }
           }
         }
       }
@@ -332,7 +351,7 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 1) tmem_dealloc_rt(tmem_base, p.tmem_cols);
 }
 
 template <int TILE_N, int STAGES>
@@ -456,18 +475,16 @@ int icf_tc_conv_forward(const icf_conv_args* a, cudaStream_t st) {
 
 namespace {
 
-template <int TILE_N, int STAGES>
-int launch_wg(const CUtensorMap& ms, const CUtensorMap& mg, const WgParams& p, dim3 grid, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (2 + TILE_N / 64) * 8192 + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<TILE_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+template <int TILE_N>
+int launch_wg(const CUtensorMap& ms, const CUtensorMap& mg, const WgParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<TILE_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     ICF_REQUIRE(e == cudaSuccess, "tensor-core wgrad: cannot reserve %zu B of shared memory: %s", smem,
                 cudaGetErrorString(e));
-    configured = true;
+    configured = smem;
   }
-  wgrad_tc_kernel<TILE_N, STAGES><<<grid, NUM_THREADS, smem, st>>>(ms, mg, p);
+  wgrad_tc_kernel<TILE_N><<<grid, NUM_THREADS, smem, st>>>(ms, mg, p);
   return icf::check_launch("wgrad_tc");
 }
 
@@ -521,8 +538,35 @@ int icf_tc_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
   p.dw = a->dw;
   const int64_t n_blocks = (int64_t)p.blocks_q * p.blocks_p * p.blocks_n;
   if (n_blocks > 0x7FFFFFFF) return -1;
-  const int64_t tiles = (int64_t)p.a_tiles * p.b_tiles * p.taps;
-  int64_t splits = (148 * 2 + tiles - 1) / tiles;       // ~2 CTAs per SM in flight
+  // taps per CTA: as many as keep >= 3 pipeline stages in ~200 KB and the accumulators in 512 TMEM columns, preferring a
+  // divisor of the tap count (ICF_WG_TP overrides, tuning aid)
+  {
+    const int nb = tile_n / 64, max_tp = 512 / tile_n;
+    int best = 1;
+    for (int tp = 1; tp <= max_tp && tp <= p.taps && tp <= 4; ++tp) {
+      const int stage = (2 + tp * nb) * 8192;
+      if (200 * 1024 / stage < 3) break;
+      if (p.taps % tp == 0 || p.taps % best != 0) best = tp;
+    }
+    static const int tp_env = []() { const char* e = getenv("ICF_WG_TP"); return e ? atoi(e) : 0; }();
+    if (tp_env > 0) {
+      best = tp_env > max_tp ? max_tp : tp_env;
+      if (best > p.taps) best = p.taps;
+      while (best > 1 && 200 * 1024 / ((2 + best * nb) * 8192) < 2) --best;
+    }
+    p.tp = best;
+    p.tap_groups = icf::cdiv(p.taps, p.tp);
+    p.stage_bytes = (uint32_t)((2 + p.tp * nb) * 8192);
+    p.stages = 200 * 1024 / (int)p.stage_bytes;
+    if (p.stages > 4) p.stages = 4;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(p.tp * tile_n)) cols <<= 1;
+    p.tmem_cols = cols;
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + 256;
+  const int ctas_per_sm = (smem <= 110 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
+  const int64_t tiles = (int64_t)p.a_tiles * p.b_tiles * p.tap_groups;
+  int64_t splits = (148 * ctas_per_sm) / tiles;          // one resident wave: never a ragged second one
   if (splits > n_blocks) splits = n_blocks;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
@@ -545,9 +589,9 @@ int icf_tc_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
   }
   dim3 grid((unsigned)tiles, (unsigned)splits);
   switch (tile_n) {
-    case 256: return launch_wg<256, 3>(ms, mg, p, grid, st);
-    case 128: return launch_wg<128, 3>(ms, mg, p, grid, st);
-    default: return launch_wg<64, 4>(ms, mg, p, grid, st);
+    case 256: return launch_wg<256>(ms, mg, p, grid, smem, st);
+    case 128: return launch_wg<128>(ms, mg, p, grid, smem, st);
+    default: return launch_wg<64>(ms, mg, p, grid, smem, st);
   }
 }
 
