@@ -129,22 +129,26 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the loop, one elected lane issues (inside an `if (lane == 0)` region
+    // every tcgen05.mma cost ~190 cycles of warp time, in warp-uniform code ~90: measured on the scatter kernel) =====
+    {
+      const uint32_t leader = elect_one();
       constexpr uint32_t idesc = make_idesc(BLOCK_M, TILE_N, 0, 0);
+      const uint64_t d0 = make_desc(0, 16, 1024);
+      const uint32_t desc_hi = (uint32_t)(d0 >> 32), desc_lo = (uint32_t)d0;      // low word without an address
       for (int iter = 0; iter < n_iters; ++iter) {
         const int s = iter % STAGES;
         mbar_wait(full_bar(s), (iter / STAGES) & 1);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
-        const uint64_t adesc = make_desc(sa, 16, 1024), bdesc = make_desc(sb, 16, 1024);
+        const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | desc_lo, b_lo = ((sb >> 4) & 0x3FFFu) | desc_lo;
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (iter | k) ? 1u : 0u);
-        umma_commit(empty_bar(s));
+          umma_bf16_lo(tmem_base, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (iter | k) ? 1u : 0u, leader);
+        umma_commit_if(empty_bar(s), leader);
       }
-      if (n_iters > 0) umma_commit(tmem_full_bar);
-      else mbar_arrive(tmem_full_bar);
+      if (n_iters > 0) umma_commit_if(tmem_full_bar, leader);
+      else if (lane == 0) mbar_arrive(tmem_full_bar);
     }
   } else {
     // ===== epilogue: one D row (TMEM lane) per thread =====
@@ -294,8 +298,12 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const uint32_t leader = elect_one();             // warp-uniform issue loop, one elected lane issues
       constexpr uint32_t idesc = make_idesc(BLOCK_M, TILE_N, 1, 1);
+      // MN-major, 128B swizzle: 64-channel chunks CHUNK_BYTES apart (LBO), 8-pixel groups 1024 B apart (SBO)
+      const uint64_t d0 = make_desc(0, CHUNK_BYTES, 1024);
+      const uint32_t desc_hi = (uint32_t)(d0 >> 32), desc_lo = (uint32_t)d0;      // low word without an address
       const int ksteps = (int)p.rows / UMMA_K;
       int st = 0;
       uint32_t ph = 0;
@@ -303,18 +311,18 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
         mbar_wait(full_bar(st), ph);
         tc_fence_after();
         const uint32_t base = smem_u32(smem) + (uint32_t)st * STAGE_BYTES;
-        // MN-major, 128B swizzle: 64-channel chunks CHUNK_BYTES apart (LBO), 8-pixel groups 1024 B apart (SBO)
-        const uint64_t adesc = make_desc(base, CHUNK_BYTES, 1024);
+        const uint32_t a_lo = ((base >> 4) & 0x3FFFu) | desc_lo;
         for (int tt = 0; tt < ntap; ++tt) {
-          const uint64_t bdesc = make_desc(base + (uint32_t)(2 + tt * NB) * CHUNK_BYTES, CHUNK_BYTES, 1024);
+          const uint32_t b_lo = (((base + (uint32_t)(2 + tt * NB) * CHUNK_BYTES) >> 4) & 0x3FFFu) | desc_lo;
           for (int k = 0; k < ksteps; ++k)   // 16 pixels = 2048 B = 128 descriptor units per step
-            umma_bf16(tmem_base + (uint32_t)(tt * TILE_N), adesc + 128 * k, bdesc + 128 * k, idesc, (i | k) ? 1u : 0u);
+            umma_bf16_lo(tmem_base + (uint32_t)(tt * TILE_N), a_lo + 128 * k, b_lo + 128 * k, desc_hi, idesc, (i | k) ? 1u : 0u,
+                         leader);
         }
-        umma_commit(empty_bar(st));
+        umma_commit_if(empty_bar(st), leader);
         if (++st == STAGES) { st = 0; ph ^= 1; }
       }
-      if (my_blocks > 0) umma_commit(tmem_full_bar);
-      else mbar_arrive(tmem_full_bar);
+      if (my_blocks > 0) umma_commit_if(tmem_full_bar, leader);
+      else if (lane == 0) mbar_arrive(tmem_full_bar);
     }
   } else {
     const int q4 = warp & 3;
