@@ -80,16 +80,17 @@ __global__ void __launch_bounds__(SC_THREADS, 1) conv_sc_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(w_bar, p.w_bytes);
-      tma_load_3d(smem_u32(wtile), &map_w, w_bar, 0, 0, 0);
+    {
+      const uint32_t leader = elect_one();              // warp-uniform loop, the elected lane issues
+      mbar_expect_tx_if(w_bar, p.w_bytes, leader);
+      tma_load_3d_if(smem_u32(wtile), &map_w, w_bar, 0, 0, 0, leader);
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x)
         for (int y = 0; y < p.H; ++y) {
           mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), SLOT_BYTES);
-          tma_load_4d(smem_u32(slots) + (uint32_t)s * SLOT_BYTES, &map_a, full_bar(s), 0, 0, y, tile * 4);
+          mbar_expect_tx_if(full_bar(s), SLOT_BYTES, leader);
+          tma_load_4d_if(smem_u32(slots) + (uint32_t)s * SLOT_BYTES, &map_a, full_bar(s), 0, 0, y, tile * 4, leader);
           if (++s == SC_SLOTS) { s = 0; ph ^= 1; }
         }
     }
@@ -285,21 +286,22 @@ __global__ void __launch_bounds__(SC_THREADS, 1) conv_sx_kernel(const __grid_con
 #define SX_WAIT(cnt, bar, par) do { if (dbg_on) { const long long t_ = clock64(); mbar_wait(bar, par); cnt += clock64() - t_; } else mbar_wait(bar, par); } while (0)
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(w_bar, p.wblk_tx * S);
-      for (int s = 0; s < S; ++s) tma_load_3d(smem_u32(wtile) + (uint32_t)s * p.wblk, &map_w, w_bar, 0, s, 0);
+    {
+      const uint32_t leader = elect_one();              // warp-uniform loop, the elected lane issues
+      mbar_expect_tx_if(w_bar, p.wblk_tx * S, leader);
+      for (int s = 0; s < S; ++s) tma_load_3d_if(smem_u32(wtile) + (uint32_t)s * p.wblk, &map_w, w_bar, 0, s, 0, leader);
       int sl = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
         const int xt = tile % p.xtiles, nt = tile / p.xtiles;
         for (int y = 0; y < p.H; ++y) {
           SX_WAIT(w0, empty_bar(sl), ph ^ 1);
-          mbar_expect_tx(full_bar(sl), SLOT_TX);
-          tma_load_4d(smem_u32(slots) + (uint32_t)sl * SLOT_BYTES, &map_a, full_bar(sl), 0, nt * SX_IMGS, xt * SX_XT - SX_PAD, y);
+          mbar_expect_tx_if(full_bar(sl), SLOT_TX, leader);
+          tma_load_4d_if(smem_u32(slots) + (uint32_t)sl * SLOT_BYTES, &map_a, full_bar(sl), 0, nt * SX_IMGS, xt * SX_XT - SX_PAD, y, leader);
           if (++sl == SX_SLOTS) { sl = 0; ph ^= 1; }
         }
       }
-      if (dbg_on) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = w0; }
+      if (dbg_on && lane == 0) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = w0; }
     }
   } else if (warp == 1) {
     {

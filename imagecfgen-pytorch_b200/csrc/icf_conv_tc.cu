@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer (warp-uniform loop, the elected lane issues) =====
+    {
+      const uint32_t leader = elect_one();
       int iter = 0;
       for (int ti_ = 0; ti_ < ntaps; ++ti_) {
         if (!tap_live(ti_)) continue;
@@ -122,9 +123,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
           const int s = iter % STAGES;
           mbar_wait(empty_bar(s), ((iter / STAGES) & 1) ^ 1);
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
-          mbar_expect_tx(full_bar(s), p.a_tx_bytes + B_BYTES);
-          tma_load_4d(sa, &map_a, full_bar(s), kc * BLOCK_K, x, y, n0);
-          tma_load_2d(sb, &map_b, full_bar(s), wcol + kc * BLOCK_K, k0);
+          mbar_expect_tx_if(full_bar(s), p.a_tx_bytes + B_BYTES, leader);
+          tma_load_4d_if(sa, &map_a, full_bar(s), kc * BLOCK_K, x, y, n0, leader);
+          tma_load_2d_if(sb, &map_b, full_bar(s), wcol + kc * BLOCK_K, k0, leader);
         }
       }
     }
@@ -273,7 +274,8 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
   const uint32_t chunk_bytes = p.rows * 128u;                    // bytes one box deposits
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const uint32_t leader = elect_one();             // warp-uniform producer loop, the elected lane issues
       int st = 0;
       uint32_t ph = 0;
       for (int i = 0; i < my_blocks; ++i) {
@@ -284,15 +286,15 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
         const int q0 = qb * p.bq, p0 = pb * p.bp, n0 = nb * p.bn;
         mbar_wait(empty_bar(st), ph ^ 1);
         const uint32_t base = smem_u32(smem) + (uint32_t)st * STAGE_BYTES;
-        mbar_expect_tx(full_bar(st), chunk_bytes * (uint32_t)(2 + ntap * NB));
-        tma_load_4d(base, &map_s, full_bar(st), a0, q0, p0, n0);
-        tma_load_4d(base + CHUNK_BYTES, &map_s, full_bar(st), a0 + 64, q0, p0, n0);
+        mbar_expect_tx_if(full_bar(st), chunk_bytes * (uint32_t)(2 + ntap * NB), leader);
+        tma_load_4d_if(base, &map_s, full_bar(st), a0, q0, p0, n0, leader);
+        tma_load_4d_if(base + CHUNK_BYTES, &map_s, full_bar(st), a0 + 64, q0, p0, n0, leader);
         for (int tt = 0; tt < ntap; ++tt) {
           const int tap = tap0 + tt, r = tap / p.S, s = tap - r * p.S;
           const int x = q0 * p.stride - p.pad + s, y = p0 * p.stride - p.pad + r;
 #pragma unroll
           for (int j = 0; j < NB; ++j)
-            tma_load_4d(base + (uint32_t)(2 + tt * NB + j) * CHUNK_BYTES, &map_g, full_bar(st), b0 + 64 * j, x, y, n0);
+            tma_load_4d_if(base + (uint32_t)(2 + tt * NB + j) * CHUNK_BYTES, &map_g, full_bar(st), b0 + 64 * j, x, y, n0, leader);
         }
         if (++st == STAGES) { st = 0; ph ^= 1; }
       }

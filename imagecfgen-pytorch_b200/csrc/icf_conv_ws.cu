@@ -186,12 +186,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
 
   if (warp == 0) {
     // ===== TMA producer: weight slab once, then the source rows of every column =====
-    if (lane == 0) {
-      mbar_expect_tx(w_full, (uint32_t)(cl.ntaps * p.kchunks) * W_BLOCK);
+    {
+      const uint32_t leader = elect_one();             // warp-uniform loop, the elected lane issues
+      mbar_expect_tx_if(w_full, (uint32_t)(cl.ntaps * p.kchunks) * W_BLOCK, leader);
       for (int t = 0; t < cl.ntaps; ++t)
         for (int kc = 0; kc < p.kchunks; ++kc)
-          tma_load_2d(slab_addr + (uint32_t)(t * p.kchunks + kc) * W_BLOCK, &map_b, w_full,
-                      cl.taps[t].widx * p.w_pitch + kc * (p.rowb >> 1), k0);
+          tma_load_2d_if(slab_addr + (uint32_t)(t * p.kchunks + kc) * W_BLOCK, &map_b, w_full,
+                         cl.taps[t].widx * p.w_pitch + kc * (p.rowb >> 1), k0, leader);
       int s = 0;
       uint32_t ph = 0;
       for (int col = r0; col < ncols; col += rstep) {
@@ -199,16 +200,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
         const int n0 = nt * p.NG, xs = jt * p.XG * p.sstep;
         for (int y = cl.ylo; y <= cl.yhi; ++y) {
           WS_TIMED_WAIT(w0, slot_empty(s), ph ^ 1);
-          mbar_expect_tx(slot_full(s), p.slot_bytes);
+          mbar_expect_tx_if(slot_full(s), p.slot_bytes, leader);
           const uint32_t base = slots_addr + (uint32_t)s * p.slot_bytes;
           for (int sub = 0; sub < p.nsub; ++sub)
             for (int kc = 0; kc < p.kchunks; ++kc)
-              tma_load_4d(base + sub * p.sub_bytes + kc * p.kc_bytes, &map_a, slot_full(s), kc * (p.rowb >> 1), n0,
-                          xs + cl.x0[sub], y);
+              tma_load_4d_if(base + sub * p.sub_bytes + kc * p.kc_bytes, &map_a, slot_full(s), kc * (p.rowb >> 1), n0,
+                             xs + cl.x0[sub], y, leader);
           if (++s == p.n_slots) { s = 0; ph ^= 1; }
         }
       }
-      if (dbg_on) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = w0; }
+      if (dbg_on && lane == 0) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = w0; }
     }
   } else if (warp <= WS_ISSUERS) {
     // ===== MMA issuers: whole warp runs the control flow, one elected lane issues.  Issuer wi owns the output rows

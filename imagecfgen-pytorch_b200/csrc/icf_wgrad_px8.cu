@@ -33,11 +33,15 @@ struct PxParams {
   float* dw;
 };
 
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
-                                            int c4) {
+__device__ __forceinline__ void tma_load_5d_if(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                               int c3, int c4, uint32_t leader) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.b32 q, %8, 0;\n"
+      "@q cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n"
+      "}\n" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(leader)
       : "memory");
 }
 
@@ -84,17 +88,18 @@ __global__ void __launch_bounds__(PX_THREADS, 1) wgrad_px8_kernel(const __grid_c
   const uint32_t smem_base = smem_u32(smem);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const uint32_t leader = elect_one();             // warp-uniform producer loop, the elected lane issues
       int s = 0;
       uint32_t ph = 0;
       const int items = p.N * p.pblocks;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
         const int n = it / p.pblocks, p0 = (it - n * p.pblocks) * p.PB;
         mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_expect_tx(full_bar(s), p.dy_bytes + p.x_bytes);
+        mbar_expect_tx_if(full_bar(s), p.dy_bytes + p.x_bytes, leader);
         const uint32_t base = smem_base + (uint32_t)s * p.slot_bytes;
-        tma_load_5d(base, &map_dy, full_bar(s), 0, 0, 0, p0, n);        // rows beyond P arrive as zeros
-        tma_load_4d(base + p.dy_bytes, &map_x, full_bar(s), 0, 0, p0, n);
+        tma_load_5d_if(base, &map_dy, full_bar(s), 0, 0, 0, p0, n, leader);        // rows beyond P arrive as zeros
+        tma_load_4d_if(base + p.dy_bytes, &map_x, full_bar(s), 0, 0, p0, n, leader);
         if (++s == PX_SLOTS) { s = 0; ph ^= 1; }
       }
     }
