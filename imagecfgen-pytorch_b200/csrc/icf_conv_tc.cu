@@ -469,7 +469,15 @@ int icf_tc_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   }
   int r;
   switch (tile_n) {
-    case 256: r = launch_tc<256, 4>(ma, mb, p, grid, st); break;
+    case 256: {
+      // 2 stages = 96 KB: two CTAs per SM, one CTA's epilogue overlaps the other's main loop.  Measured: 8-18 % faster when
+      // the grid is at least ~1.5 waves (G.layers.2 fprop, the 256-wide dgrads, the 771->4608 GEMM), 20-40 % slower on the
+      // 64-128 CTA grids of the 1x1-spatial layers, which keep the 4-stage ring (ICF_TC_256_STAGES=2|4 forces either)
+      static const int st_env = []() { const char* e = getenv("ICF_TC_256_STAGES"); return e ? atoi(e) : 0; }();
+      const bool two = st_env == 2 || (st_env != 4 && grid >= 220);
+      r = two ? launch_tc<256, 2>(ma, mb, p, grid, st) : launch_tc<256, 4>(ma, mb, p, grid, st);
+      break;
+    }
     case 128: r = launch_tc<128, 3>(ma, mb, p, grid, st); break;
     case 64: r = launch_tc<64, 4>(ma, mb, p, grid, st); break;
     default: r = launch_tc<32, 4>(ma, mb, p, grid, st); break;
