@@ -495,8 +495,10 @@ int launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& m
 
 }  // namespace
 
-// returns 0 = launched, -1 = geometry outside this kernel's envelope (caller tries the next kernel), >0 = error
-int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
+namespace {
+// returns 0 = launched (or, with `plan`, described), -1 = geometry outside this kernel's envelope (caller tries the
+// next kernel), >0 = error
+int ws_forward_impl(const icf_conv_args* a, cudaStream_t st, int32_t* plan, int32_t plan_words) {
   if (a->dtype != ICF_BF16 || a->accumulate) return -1;
   if ((a->in_pitch & 7) || (a->w_pitch & 7)) return -1;
   if (a->win > 1 && a->pad != 0) return -1;
@@ -699,6 +701,28 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   }();
   q.dbg = dbg_buf;
 
+  if (plan) {
+    // ---- icf_ws_plan: describe instead of launching (layout documented in include/icf.h) ----
+    const int need = 16 + WS_MAX_CLASSES * 48 + WS_PROG_WORDS;
+    if (plan_words < need) { icf::set_error("icf_ws_plan: out needs %d words", need); return 1; }
+    memset(plan, 0, sizeof(int32_t) * (size_t)need);
+    plan[0] = q.n_classes; plan[1] = q.XG; plan[2] = q.NG; plan[3] = q.n_slots; plan[4] = q.n_acc; plan[5] = tile_n;
+    plan[6] = q.sstep; plan[7] = q.ostep; plan[8] = WS_ISSUERS; plan[9] = q.cls[q.n_classes - 1].prog_off[WS_ISSUERS];
+    plan[10] = grid; plan[11] = q.tiles_k; plan[12] = q.tiles_n; plan[13] = (int32_t)prog_bytes;
+    for (int c = 0; c < q.n_classes; ++c) {
+      const WsClass& cl = q.cls[c];
+      int32_t* o = plan + 16 + 48 * c;
+      o[0] = cl.Pi; o[1] = cl.Qj; o[2] = cl.py; o[3] = cl.px; o[4] = cl.ylo; o[5] = cl.yhi; o[6] = cl.dymax; o[7] = cl.ngroups;
+      o[8] = cl.ntaps; o[9] = cl.tiles_x; o[10] = cl.cta_begin; o[11] = cl.cta_count;
+      for (int wi = 0; wi <= WS_ISSUERS; ++wi) o[12 + wi] = cl.prog_off[wi];
+      for (int g = 0; g < cl.ngroups; ++g) {
+        o[16 + 4 * g] = cl.grp[g].dy; o[17 + 4 * g] = cl.grp[g].dprev; o[18 + 4 * g] = cl.grp[g].first; o[19 + 4 * g] = cl.grp[g].count;
+      }
+    }
+    for (int w = 0; w < plan[9]; ++w) plan[16 + WS_MAX_CLASSES * 48 + w] = (int32_t)q.prog[w];
+    return 0;
+  }
+
   CUtensorMap ma, mb, mo;
   memset(&mo, 0, sizeof(mo));
   // TMA-store epilogue: bf16 destination whose pixels are 16-byte aligned rows (pitch % 8 == 0)
@@ -776,3 +800,12 @@ int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   }
   return 0;
 }
+}  // namespace
+
+int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t st) { return ws_forward_impl(a, st, nullptr, 0); }
+
+int icf_ws_plan(const icf_conv_args* a, int32_t* out, int32_t out_words) {
+  ICF_REQUIRE(a && out && out_words > 0, "icf_ws_plan: bad arguments");
+  return ws_forward_impl(a, nullptr, out, out_words);
+}
+

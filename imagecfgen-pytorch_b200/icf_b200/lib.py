@@ -87,6 +87,7 @@ _SIGS = {
     "icf_tc_enabled": (_i32, []),
     "icf_set_tc_enabled": (None, [_i32]),
     "icf_last_conv_path": (_i32, []),
+    "icf_ws_plan": (_i32, [C.POINTER(ConvArgs), C.POINTER(C.c_int32), _i32]),
     "icf_conv_forward": (_i32, [C.POINTER(ConvArgs), _vp]),
     "icf_conv_wgrad": (_i32, [C.POINTER(WgradArgs), _vp]),
     "icf_pack": (_i32, [_vp, _vp, _i32, C.POINTER(Perm), _vp]),

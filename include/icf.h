@@ -81,6 +81,20 @@ typedef struct icf_conv_args {
 } icf_conv_args;
 int icf_conv_forward(const icf_conv_args* a, void* stream);
 
+/* Introspection / test hook, no kernel launch and no GPU needed: the plan the weight-stationary row-streaming kernel
+ * would use for `a` (pointers in `a` only need to be 16-byte aligned, they are not dereferenced).  Returns 0 and fills
+ * `out`, -1 when the geometry is outside that kernel's envelope, > 0 on error.  `out` needs 16 + 4*48 + 1536 int32 words:
+ *   [0] classes (output-parity classes of a transposed conv, else 1)  [1] XG  [2] NG  (a column = XG output columns x NG
+ *   images = 128 MMA rows)  [3] ring slots  [4] TMEM accumulators  [5] channel tile  [6] source step  [7] output step
+ *   [8] issuer warps  [9] schedule words in total  [10] grid  [11] channel tiles  [12] image groups  [13] schedule bytes in smem
+ *   per class c at [16 + 48*c]: Pi, Qj, py, px, ylo, yhi, dymax, groups, taps, x tiles, first CTA, CTAs,
+ *                               schedule offsets of issuer 0..issuers (end), then per group g at [+16+4g]: dy, dprev, first tap, taps
+ *   schedule words at [16 + 4*48]: bits 0-7 output row | 8-12 first tap | 13-17 tap count | 18-19 kind (0 MMA chain,
+ *                               1 accumulator complete, 2 nothing) | 20 chain opens the accumulator | 21 last action of its source row;
+ *                               every issuer's list ends with one spare word.
+ * tests/test_host_cpu.py replays the schedules and checks the accumulator protocol for every layer of every family. */
+int icf_ws_plan(const icf_conv_args* a, int32_t* out, int32_t out_words);
+
 /* Weight gradient (the wgrad half of aten::convolution_backward), fp32 accumulation, split over pixels:
  *   dw[a][r*S+s][b] += sum_{n,p,q} small[n,p,q,a] * big[n, p*stride-pad+r, q*stride-pad+s, b]
  * Conv2d: small = dY, big = X.  ConvTranspose2d: small = X, big = dY. */

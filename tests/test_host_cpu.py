@@ -113,6 +113,119 @@ def test_flop_accounting_matches_survey():
     assert abs(f["E"] / 1e6 - 1293.2) < 0.5 and abs(f["G"] / 1e6 - 1534.3) < 0.5 and abs(f["D"] / 1e6 - 1298.5) < 0.5
 
 
+def _ws_plan(a):
+    """(header, classes, schedule words) of the row-streaming kernel for ConvArgs `a`, or None if it declines."""
+    from icf_b200 import lib
+    words = 16 + 4 * 48 + 1536
+    out = (ctypes.c_int32 * words)()
+    rc = lib.load().icf_ws_plan(ctypes.byref(a), out, words)
+    if rc == -1:
+        return None
+    assert rc == 0, lib.load().icf_last_error()
+    o = list(out)
+    classes = []
+    for c in range(o[0]):
+        b = 16 + 48 * c
+        cl = dict(zip(("Pi", "Qj", "py", "px", "ylo", "yhi", "dymax", "ngroups", "ntaps", "tiles_x", "cta_begin", "cta_count"),
+                      o[b:b + 12]))
+        cl["prog_off"] = o[b + 12:b + 12 + o[8] + 1]
+        cl["groups"] = [tuple(o[b + 16 + 4 * g:b + 20 + 4 * g]) for g in range(cl["ngroups"])]
+        classes.append(cl)
+    return o[:16], classes, o[16 + 4 * 48:16 + 4 * 48 + o[9]]
+
+
+def _check_ws_schedule(hdr, classes, prog):
+    """Replay every issuer's schedule of every class and check the accumulator protocol the kernel relies on."""
+    n_acc, sstep, issuers = hdr[4], hdr[6], hdr[8]
+    assert hdr[1] * hdr[2] == 128 and hdr[3] >= 2 and sum(c["cta_count"] for c in classes) == hdr[10] <= 148
+    for cl in classes:
+        Pi, ylo, yhi = cl["Pi"], cl["ylo"], cl["yhi"]
+        dys = [g[0] for g in cl["groups"]]
+        # ground truth: which (source row, group) pairs feed which output row
+        feeds = {}
+        for y in range(ylo, yhi + 1):
+            for gi, dy in enumerate(dys):
+                num = y - dy
+                if num < 0 or num % sstep:
+                    continue
+                i = num // sstep
+                if i < Pi:
+                    feeds.setdefault(i, []).append((y, gi))
+        assert sorted(feeds) == list(range(Pi)), "every output row needs a source row"
+        seen, opened, completed = {}, {}, {}
+        for wi in range(issuers):
+            words = prog[cl["prog_off"][wi]:cl["prog_off"][wi + 1]]
+            assert (words[-1] >> 18) & 3 == 2, "spare word at the end of an issuer's list"
+            y, k = ylo, 0
+            while y <= yhi:
+                w = words[k]
+                k += 1
+                i, first, cnt, kind = w & 0xFF, (w >> 8) & 31, (w >> 13) & 31, (w >> 18) & 3
+                if kind == 0:
+                    assert i % issuers == wi, "an accumulator is fed by one issuer only"
+                    gi = next(g for g, grp in enumerate(cl["groups"]) if grp[2] == first and grp[3] == cnt)
+                    assert (y, gi) in feeds[i] and (i, y, gi) not in seen
+                    seen[(i, y, gi)] = True
+                    assert i not in completed, "no chain after the accumulator was handed to the epilogue"
+                    if (w >> 20) & 1:
+                        assert i not in opened
+                        opened[i] = y
+                    else:
+                        assert i in opened, "first chain of an output row must clear the accumulator"
+                elif kind == 1:
+                    assert i % issuers == wi and i in opened and i not in completed
+                    completed[i] = y
+                if (w >> 21) & 1:
+                    y += 1
+            assert k == len(words) - 1
+        assert len(seen) == sum(len(v) for v in feeds.values()), "every contribution issued exactly once"
+        for i in range(Pi):
+            assert opened[i] == min(y for y, _ in feeds[i]) and completed[i] >= max(y for y, _ in feeds[i])
+        # output rows in flight at any source row never exceed the accumulator ring minus the one being drained
+        for y in range(ylo, yhi + 1):
+            live = sum(1 for i in range(Pi) if opened[i] <= y <= completed[i])
+            assert live <= n_acc - 1, (live, n_acc)
+
+
+@pytest.mark.parametrize("fam", ["mnist", "audio_mnist", "whalecalls", "esrf_acoustic"])
+def test_row_streaming_schedules_replay(fam):
+    """Host logic of the weight-stationary kernel (icf_ws_plan, no launch): for every conv layer of the family, forward
+    and data-gradient form, the issuer schedules must issue every (source row, filter row) contribution exactly once,
+    from the issuer that owns the output row, clear each accumulator on its first chain and hand it over after its last."""
+    from icf_b200 import lib
+    from icf_b200.arch import FAMILIES
+
+    def pad8(c):
+        return (c + 7) // 8 * 8
+
+    f = FAMILIES[fam]
+    N, served = 256, 0
+    for tower, h0 in (("E", f.image), ("G", (1, 1)), ("Dx", f.image)):
+        h, w = h0
+        for li, sp in enumerate(getattr(f, tower)):
+            if sp.kind not in ("conv", "convT"):
+                continue
+            if sp.kind == "conv":
+                P, Q = (h + 2 * sp.pad - sp.k) // sp.stride + 1, (w + 2 * sp.pad - sp.k) // sp.stride + 1
+                form_f, form_b = lib.FORM_GATHER, lib.FORM_TRANSPOSED
+            else:
+                P, Q = (h - 1) * sp.stride - 2 * sp.pad + sp.k, (w - 1) * sp.stride - 2 * sp.pad + sp.k
+                form_f, form_b = lib.FORM_TRANSPOSED, lib.FORM_GATHER
+            cases = [(form_f, h, w, sp.cin, P, Q, sp.cout, sp.k, sp.k, sp.stride, sp.pad, 0),
+                     (form_b, P, Q, sp.cout, h, w, sp.cin, sp.k, sp.k, sp.stride, sp.pad, 0)]
+            if li == 0 and tower in ("E", "Dx"):     # folded first layer: filter columns live in the channel dimension
+                cases.append((form_f, h + 2 * sp.pad, w + 2 * sp.pad, sp.k * 8, P, Q, sp.cout, sp.k, 1, sp.stride, 0, sp.k))
+            for form, H, W, Cc, Po, Qo, K, R, S, stride, pad, win in cases:
+                a = lib.ConvArgs(lib.BF16, form, N, H, W, Cc, 8 if win else pad8(Cc), Po, Qo, K, pad8(K), R, S, stride, pad,
+                                 K, pad8(Cc), 0, 0.0, 0, 0, 0, win, 0x10000, 0x20000, None, 0x30000, None, None)
+                plan = _ws_plan(a)
+                if plan is not None:
+                    _check_ws_schedule(*plan)
+                    served += 1
+            h, w = P, Q
+    assert served > 0 or fam == "esrf_acoustic"
+
+
 _WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
