@@ -532,7 +532,9 @@ void pick_kblock(int N, int P, int Q, int* bq_, int* bp_, int* bn_) {
 
 }  // namespace
 
-int icf_tc_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
+namespace {
+// returns 0 = launched (or, with `plan`, described), -1 = not this kernel's case, > 0 = error
+int wgrad_impl(const icf_wgrad_args* a, cudaStream_t st, int32_t* plan, int32_t plan_words) {
   if (a->dtype != ICF_BF16) return -1;
   if ((a->a_pitch & 7) || (a->b_pitch & 7)) return -1;
   if ((reinterpret_cast<uintptr_t>(a->small_t) & 15) || (reinterpret_cast<uintptr_t>(a->big_t) & 15)) return -1;
@@ -588,6 +590,14 @@ int icf_tc_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
   if (splits > n_blocks) splits = n_blocks;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
+  if (plan) {     // icf_wgrad_plan: describe instead of launching (layout in include/icf.h)
+    if (plan_words < 16) { icf::set_error("icf_wgrad_plan: out needs 16 words"); return 1; }
+    const int32_t v[16] = {tile_n, p.tp, p.tap_groups, p.stages, (int32_t)p.stage_bytes, (int32_t)p.tmem_cols, (int32_t)smem,
+                           ctas_per_sm, (int32_t)tiles, (int32_t)splits, p.bq, p.bp, p.bn, (int32_t)p.rows, (int32_t)n_blocks,
+                           p.taps};
+    for (int i = 0; i < 16; ++i) plan[i] = v[i];
+    return 0;
+  }
   CUtensorMap ms, mg;
   {
     cuuint64_t dims[4] = {(cuuint64_t)a->A, (cuuint64_t)a->Q, (cuuint64_t)a->P, (cuuint64_t)a->N};
@@ -611,5 +621,13 @@ int icf_tc_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
     case 128: return launch_wg<128>(ms, mg, p, grid, smem, st);
     default: return launch_wg<64>(ms, mg, p, grid, smem, st);
   }
+}
+}  // namespace
+
+int icf_tc_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) { return wgrad_impl(a, st, nullptr, 0); }
+
+int icf_wgrad_plan(const icf_wgrad_args* a, int32_t* out, int32_t out_words) {
+  ICF_REQUIRE(a && out && out_words > 0, "icf_wgrad_plan: bad arguments");
+  return wgrad_impl(a, nullptr, out, out_words);
 }
 

@@ -90,6 +90,7 @@ _SIGS = {
     "icf_ws_plan": (_i32, [C.POINTER(ConvArgs), C.POINTER(C.c_int32), _i32]),
     "icf_conv_forward": (_i32, [C.POINTER(ConvArgs), _vp]),
     "icf_conv_wgrad": (_i32, [C.POINTER(WgradArgs), _vp]),
+    "icf_wgrad_plan": (_i32, [C.POINTER(WgradArgs), C.POINTER(C.c_int32), _i32]),
     "icf_pack": (_i32, [_vp, _vp, _i32, C.POINTER(Perm), _vp]),
     "icf_pack_multi": (_i32, [_vp, _i32, _i64, _vp]),
     "icf_unpack_multi": (_i32, [_vp, _i32, _i64, _vp]),

@@ -111,6 +111,13 @@ typedef struct icf_wgrad_args {
 } icf_wgrad_args;
 int icf_conv_wgrad(const icf_wgrad_args* a, void* stream);
 
+/* Introspection / test hook like icf_ws_plan, for the tensor-core weight-gradient kernel (no launch, no GPU needed; returns
+ * -1 when that kernel declines the geometry).  `out` (>= 16 int32 words): [0] channel tile of the big operand  [1] taps per
+ * CTA  [2] tap groups  [3] pipeline stages  [4] bytes per stage  [5] TMEM columns  [6] dynamic shared memory  [7] CTAs per SM
+ * assumed  [8] grid.x = channel tiles x tap groups  [9] grid.y = split of the pixel blocks  [10..12] pixel-block box
+ * (columns, rows, images)  [13] pixels per block  [14] pixel blocks  [15] taps */
+int icf_wgrad_plan(const icf_wgrad_args* a, int32_t* out, int32_t out_words);
+
 /* ------------------------------------------------------------------------------------------------
  * Weight (re)packing between the checkpoint layout (fp32 OIHW / IOHW / [out,in], App. A.5 of SURVEY.md)
  * and the K-major operand layout the conv kernels read.  Generic 3-index permutation:

@@ -226,6 +226,55 @@ def test_row_streaming_schedules_replay(fam):
     assert served > 0 or fam == "esrf_acoustic"
 
 
+@pytest.mark.parametrize("fam", ["mnist", "audio_mnist", "whalecalls", "esrf_acoustic"])
+@pytest.mark.parametrize("batch", [64, 4096])
+def test_wgrad_plans_fit_the_machine(fam, batch):
+    """Host logic of the tensor-core weight-gradient kernel (icf_wgrad_plan, no launch): tap groups cover the taps, the
+    accumulators fit TMEM, the stage ring fits shared memory at the assumed CTAs per SM, and the grid is one resident wave
+    (a ragged second wave cost 20-30 %)."""
+    from icf_b200 import lib
+    from icf_b200.arch import FAMILIES
+
+    def pad8(c):
+        return (c + 7) // 8 * 8
+
+    f = FAMILIES[fam]
+    served = 0
+    for tower, h0 in (("E", f.image), ("G", (1, 1)), ("Dx", f.image)):
+        h, w = h0
+        for sp in getattr(f, tower):
+            if sp.kind not in ("conv", "convT"):
+                continue
+            if sp.kind == "conv":
+                P, Q = (h + 2 * sp.pad - sp.k) // sp.stride + 1, (w + 2 * sp.pad - sp.k) // sp.stride + 1
+                small, big = (P, Q, sp.cout), (h, w, sp.cin)          # dY is the small operand, X the strided one
+            else:
+                P, Q = (h - 1) * sp.stride - 2 * sp.pad + sp.k, (w - 1) * sp.stride - 2 * sp.pad + sp.k
+                small, big = (h, w, sp.cin), (P, Q, sp.cout)          # transposed conv: roles swap
+            a = lib.WgradArgs(lib.BF16, batch, small[0], small[1], small[2], pad8(small[2]), big[0], big[1], big[2],
+                              pad8(big[2]), sp.k, sp.k, sp.stride, sp.pad, 0x10000, 0x20000, 0x30000, 0)
+            out = (ctypes.c_int32 * 16)()
+            rc = lib.load().icf_wgrad_plan(ctypes.byref(a), out, 16)
+            h, w = P, Q
+            if rc == -1:
+                continue
+            assert rc == 0, lib.load().icf_last_error()
+            (tile_n, tp, groups, stages, stage_bytes, cols, smem, ctas, tiles, splits, bq, bp, bn, rows, n_blocks,
+             taps) = list(out)
+            served += 1
+            assert taps == sp.k * sp.k and (groups - 1) * tp < taps <= groups * tp
+            assert cols >= tp * tile_n and cols & (cols - 1) == 0 and ctas * cols <= 512
+            assert stages >= 2 and smem == stages * stage_bytes + 1280 and ctas * smem <= 227 * 1024
+            assert stage_bytes == (2 + tp * tile_n // 64) * 8192
+            assert rows == bq * bp * bn and rows in (16, 32, 48, 64)
+            assert n_blocks == -(-small[1] // bq) * -(-small[0] // bp) * -(-batch // bn)
+            assert 1 <= splits <= n_blocks
+            assert tiles * splits <= 148 * ctas or splits == 1, "one resident wave"
+            if tiles <= 148 * ctas and n_blocks >= 148 * ctas:      # floor(capacity / tiles) keeps more than half the slots busy
+                assert tiles * splits > 148 * ctas // 2, "grid should fill at least half the machine"
+    assert served > 0
+
+
 _WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
