@@ -340,15 +340,16 @@ __global__ void act_backward_kernel(const icf_actbwd_args a) {
     float g_scale = 1.f, m0 = 0.f, m1 = 0.f, mu = 0.f, is = 0.f;
     const bool bn = a.bn_sums != nullptr;
     if (bn) {
-      const float invM = 1.f / (float)a.pixels;
+      const float iw = a.bn_inv_world > 0.f ? a.bn_inv_world : 1.f;
+      const float invM = iw / (float)a.pixels;
       mu = a.bn_mean[c];
       is = a.bn_invstd[c];
       g_scale = a.bn_gamma[c] * is;
       m0 = a.bn_sums[c] * invM;
       m1 = a.bn_sums[a.C + c] * invM;
       if (blockIdx.y == 0 && py == 0) {
-        if (a.bn_dgamma) a.bn_dgamma[c] += a.bn_sums[a.C + c];
-        if (a.bn_dbeta) a.bn_dbeta[c] += a.bn_sums[c];
+        if (a.bn_dgamma) a.bn_dgamma[c] += a.bn_sums[a.C + c] * iw;
+        if (a.bn_dbeta) a.bn_dbeta[c] += a.bn_sums[c] * iw;
       }
     }
     for (int64_t pix = (int64_t)blockIdx.y * 8 + py; pix < a.pixels; pix += (int64_t)gridDim.y * 8) {
@@ -667,7 +668,8 @@ __global__ void __launch_bounds__(VT, 2) act_backward_v8(const icf_actbwd_args a
     //   gamma*invstd*(g - m0 - (y - mu)*invstd*m1)  =  cA*g + cB*y + cC
     V8 cA, cB, cC;
     if (bn) {
-      const float invM = 1.f / (float)a.pixels;
+      const float iw = a.bn_inv_world > 0.f ? a.bn_inv_world : 1.f;
+      const float invM = iw / (float)a.pixels;
       const V8 mu = ldf8(a.bn_mean + m.c0), is = ldf8(a.bn_invstd + m.c0);
       const V8 ga = ldf8(a.bn_gamma + m.c0), s0 = ldf8(a.bn_sums + m.c0), s1 = ldf8(a.bn_sums + a.C + m.c0);
 #pragma unroll
@@ -680,8 +682,8 @@ __global__ void __launch_bounds__(VT, 2) act_backward_v8(const icf_actbwd_args a
       if (m.pix0 == 0) {            // exactly one thread per channel group has pix0 == 0
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if (a.bn_dgamma) a.bn_dgamma[m.c0 + j] += s1.v[j];
-          if (a.bn_dbeta) a.bn_dbeta[m.c0 + j] += s0.v[j];
+          if (a.bn_dgamma) a.bn_dgamma[m.c0 + j] += s1.v[j] * iw;
+          if (a.bn_dbeta) a.bn_dbeta[m.c0 + j] += s0.v[j] * iw;
         }
       }
     }

@@ -47,6 +47,7 @@ class Family:
     adam_betas: Tuple[float, float]
     default_batch: int
     emb_decl: Tuple[str, ...] = ()     # order in which the reference constructor registers the embeddings
+    d_decl: Tuple[str, ...] = ("Dz", "Dx", "Dxz")   # order in which the reference Discriminator registers its towers
 
 
 def _lr(s):
@@ -129,7 +130,8 @@ ESRF = Family(
     E=_tower("layers", [3, _d, 2 * _d, 4 * _d, 8 * _d, 16 * _d, 32 * _d, 64 * _d, 512]),
     G=_gen(512 + 257, [16 * _d, 16 * _d, 8 * _d, 4 * _d, 2 * _d, _d, _d, 1]),
     Dx=_tower("dx", [3, _d, 2 * _d, 4 * _d, 8 * _d, 16 * _d, 32 * _d, 64 * _d, 512]),
-    Dz=_DZ, Dxz=_DXZ, init_std=0.001, adam_betas=(0.5, 0.9), default_batch=64, emb_decl=("has_boat",))
+    Dz=_DZ, Dxz=_DXZ, init_std=0.001, adam_betas=(0.5, 0.9), default_batch=64, emb_decl=("has_boat",),
+    d_decl=("Dx", "Dz", "Dxz"))                            # esrf_acoustic.py:218-241 declares dx before dz
 
 FAMILIES: Dict[str, Family] = {f.name: f for f in (MNIST, AUDIO_MNIST, WHALE, ESRF)}
 

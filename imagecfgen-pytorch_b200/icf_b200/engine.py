@@ -325,6 +325,9 @@ class NetExec:
         self._wg_table = None
         self._wg_key = None
         self._scratch = None
+        self.bn_sync = None                         # icf_b200.dp.Group: BatchNorm statistics span all ranks (SyncBN)
+        self.keep_state = False                     # tests: keep the saved activations of the last forward
+        self.last_state = None
         self.emb_key = 2 if role != "G" else 3      # index into fam.cat_attrs tuples
 
     # ---- parameters -----------------------------------------------------------------------------
@@ -425,7 +428,11 @@ class NetExec:
                 ss = torch.empty(4 * K, dtype=torch.float32, device=self.device)   # scale|shift|mean|invstd
                 if training:
                     nbt = ts.get(sp.bn + ".num_batches_tracked")
-                    ops.bn_finalize(stats, K, pix, gamma.data_ptr(), beta.data_ptr(), 1e-5, 0.1, rm.data_ptr(),
+                    count = pix
+                    if self.bn_sync is not None:         # SyncBN: sum / sum of squares over the whole (global) batch
+                        self.bn_sync.all_reduce(tw.stats[i])
+                        count = pix * self.bn_sync.world
+                    ops.bn_finalize(stats, K, count, gamma.data_ptr(), beta.data_ptr(), 1e-5, 0.1, rm.data_ptr(),
                                     rv.data_ptr(), ops.ptr(nbt), ops.ptr(ss), ops.ptr(ss, K), ops.ptr(ss, 2 * K),
                                     ops.ptr(ss, 3 * K))
                 else:
@@ -477,7 +484,11 @@ class NetExec:
                 bm_ptr, bm_pitch = (ops.ptr(bm), bm.shape[1]) if bm is not None else (None, 0)
                 ops.bn_bwd_reduce(g.ptr, g.code, g.pitch, y.ptr, y.code, y.pitch, pix, pps, K, bm_ptr, bm_pitch,
                                   ops.ptr(ss, 2 * K), ops.ptr(ss, 3 * K), sums.data_ptr())
-                kw = dict(bn_sums=sums.data_ptr(), bn_mask=bm_ptr, bn_mask_pitch=bm_pitch,
+                inv_world = 0.0
+                if self.bn_sync is not None:
+                    self.bn_sync.all_reduce(sums)
+                    inv_world = 1.0 / self.bn_sync.world
+                kw = dict(bn_sums=sums.data_ptr(), bn_mask=bm_ptr, bn_mask_pitch=bm_pitch, bn_inv_world=inv_world,
                           bn_gamma=ts[sp.bn + ".weight"].data_ptr(), bn_mean=ops.ptr(ss, 2 * K),
                           bn_invstd=ops.ptr(ss, 3 * K),
                           bn_dgamma=ops.ptr(grads[sp.bn + ".weight"]) if grads is not None else None,
@@ -587,7 +598,10 @@ class NetExec:
         self.repack()
         feat, fstate = self._image_feats(N, x_ptr, x_code, x_pitch, c, None)
         out, saved = self._tower_fwd("E", N, feat, {}, True, save)
-        return out, {"N": N, "feat": fstate, "tower": saved}
+        st = {"N": N, "feat": fstate, "tower": saved}
+        if self.keep_state:
+            self.last_state = st
+        return out, st
 
     def encoder_backward(self, st, dout: Act, grads, need_dX=False):
         if grads is not None:
@@ -619,7 +633,10 @@ class NetExec:
                             [a[1] for a in self.fam.cat_attrs], [t.data_ptr() for t in tables],
                             [t.data_ptr() for t in onehots], [t.data_ptr() for t in conts], lat.ptr)
         out, saved = self._tower_fwd("G", N, lat, {}, True, save)
-        return out, {"N": N, "onehots": onehots, "conts": conts, "tower": saved}
+        st = {"N": N, "onehots": onehots, "conts": conts, "tower": saved}
+        if self.keep_state:
+            self.last_state = st
+        return out, st
 
     def generator_backward(self, st, dout: Act, grads, need_dz=False, need_dattr=False):
         """-> (dz fp32 [N,latent] | None, [d_onehot per cat attr] | None, [d_cont per cont attr] | None)."""
@@ -684,7 +701,10 @@ class NetExec:
         _, sz = self._tower_fwd("Dz", N, zin, per["Dz"], training, save, final=Act(cat, kz, kx),
                                 final_mask=(cm, kx) if cm is not None else None)
         logits, sxz = self._tower_fwd("Dxz", N, Act(cat, kx + kz), per["Dxz"], training, save, final_f32=True)
-        return logits, {"N": N, "feat": fstate, "Dx": sx, "Dz": sz, "Dxz": sxz, "zmask": zm, "cat": cat}
+        st = {"N": N, "feat": fstate, "Dx": sx, "Dz": sz, "Dxz": sxz, "zmask": zm, "cat": cat}
+        if self.keep_state:
+            self.last_state = st
+        return logits, st
 
     def discriminator_backward(self, st, dlogits: Act, grads, need_dX=False, need_dz=False):
         """-> (dX fp32 [N*H*W,1] | None, dz fp32 [N,latent] | None)."""

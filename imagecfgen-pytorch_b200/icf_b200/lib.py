@@ -78,7 +78,7 @@ class ActBwdArgs(C.Structure):
                 ("dOut", _vp), ("y", _vp), ("dPre", _vp), ("out_mask", _vp), ("dbias", _vp),
                 ("bias_mod", _i32),
                 ("bn_sums", _vp), ("bn_mask", _vp), ("bn_gamma", _vp), ("bn_mean", _vp),
-                ("bn_invstd", _vp), ("bn_dgamma", _vp), ("bn_dbeta", _vp)]
+                ("bn_invstd", _vp), ("bn_dgamma", _vp), ("bn_dbeta", _vp), ("bn_inv_world", _f32)]
 
 
 _SIGS = {

@@ -226,6 +226,10 @@ class _BiGANNet(nn.Module):
     """Common base: parameter construction from the family table + engine cache."""
     FAMILY: str = ""
     ROLE: str = ""
+    # class-level defaults: a whole-module pickle written by the REFERENCE (train_mnist_image_scm.py:61-67,
+    # train_esrf_bigan.py:31-35) unpickles into these classes without running __init__, i.e. without the two attributes
+    compute_dtype: str = DEFAULT_DTYPE
+    _exec = None
 
     def __init__(self):
         super().__init__()
@@ -238,7 +242,7 @@ class _BiGANNet(nn.Module):
             key = a[emb_idx]
             assert key.endswith(".weight")
             _attach(self, key[:-len(".weight")], EmbeddingParams(a[1]))
-        towers = {"E": ("E",), "G": ("G",), "D": ("Dz", "Dx", "Dxz")}[role]   # mnist.py:98-136 declares dz first
+        towers = {"E": ("E",), "G": ("G",), "D": fam.d_decl}[role]   # mnist.py:98-136 declares dz first, ESRF dx first
         for t in towers:
             for l in getattr(fam, t):
                 _attach(self, l.key, _layer_params(l))

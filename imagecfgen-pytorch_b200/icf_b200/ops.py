@@ -249,10 +249,10 @@ def bn_bwd_reduce(dU, d_dtype, d_pitch, y, y_dtype, y_pitch, pixels, pps, Cc, ma
 
 def act_backward(dOut, d_dtype, d_pitch, y, y_dtype, y_pitch, dPre, p_dtype, p_pitch, pixels, pps, Cc, act,
                  slope, out_mask=None, mask_pitch=0, dbias=None, bn_sums=None, bn_mask=None, bn_mask_pitch=0,
-                 bn_gamma=None, bn_mean=None, bn_invstd=None, bn_dgamma=None, bn_dbeta=None):
+                 bn_gamma=None, bn_mean=None, bn_invstd=None, bn_dgamma=None, bn_dbeta=None, bn_inv_world=0.0):
     a = _l.ActBwdArgs(d_dtype, d_pitch, y_dtype, y_pitch, p_dtype, p_pitch, pixels, pps, Cc, ACT[act], slope,
                       mask_pitch, bn_mask_pitch, dOut, y, dPre, out_mask, dbias, 0, bn_sums, bn_mask, bn_gamma,
-                      bn_mean, bn_invstd, bn_dgamma, bn_dbeta)
+                      bn_mean, bn_invstd, bn_dgamma, bn_dbeta, bn_inv_world)
     es = lambda d: 4 if d == F32 else 2
     _launch("icf_act_backward", _l.load().icf_act_backward, C.byref(a),
             nbytes=float(pixels) * Cc * (es(d_dtype) + es(y_dtype) + es(p_dtype)),

@@ -18,6 +18,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
+from .dp import Group
 from .engine import Act, NetExec, draw_masks, dtype_code
 
 F32 = ops.F32
@@ -53,7 +54,12 @@ class _FlatGroup:
 
 class BiGANTrainer:
     def __init__(self, E, G, D, lr=1e-4, betas=None, eps=1e-8, dtype=None, process_group=None,
-                 overlap_allreduce=True):
+                 overlap_allreduce=True, sync_bn=False, broadcast=True, rank_rng=True):
+        """``process_group``: data parallelism over its ranks (one process per GPU).  Rank 0's parameters and buffers are
+        broadcast so that all replicas start identical (``broadcast``), every rank but 0 re-seeds its device generator so
+        that z / Dropout2d masks differ per rank (``rank_rng``), gradients are averaged once per optimiser step, and with
+        ``sync_bn`` the Discriminator's BatchNorm statistics span the global batch (the reference's semantics at batch
+        B*world, mnist.py:111-122) instead of the local shard (standard DDP semantics = the reference at batch B)."""
         self.E, self.G, self.D = E, G, D
         if dtype is not None:
             for m in (E, G, D):
@@ -71,7 +77,15 @@ class BiGANTrainer:
         self.gradsG = {n[2:]: v for n, v in self.gEG.grad_views.items() if n.startswith("G.")}
         self.gradsD = {n[2:]: v for n, v in self.gD.grad_views.items()}
         self.pg = process_group
-        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.group = Group(process_group)
+        self.world, self.rank = self.group.world, self.group.rank
+        if self.world > 1:
+            if broadcast:
+                self.group.broadcast_state([self.gEG.flat, self.gD.flat] + [b for m in (E, G, D) for b in m.buffers()])
+            if rank_rng:
+                self.group.seed_offset(self.device)
+        self.sync_bn = bool(sync_bn) and self.world > 1
+        self.exD.bn_sync = self.group if self.sync_bn else None
         gs = 1.0 / self.world
         self.stateEG = torch.tensor([0, lr, betas[0], betas[1], eps, gs, 0, 0], dtype=torch.float32, device=self.device)
         self.stateD = self.stateEG.clone()
@@ -100,6 +114,23 @@ class BiGANTrainer:
             return done
         dist.all_reduce(buf, group=self.pg)
         return None
+
+    def reduce_scores(self, scores: torch.Tensor) -> torch.Tensor:
+        """Per-epoch score / loss accumulators averaged over the ranks (one tiny all-reduce per epoch)."""
+        if self.world > 1:
+            scores = scores.clone()
+            self.group.all_reduce(scores)
+            scores /= self.world
+        return scores
+
+    def finish(self):
+        """End of training: with per-rank BatchNorm statistics the running buffers of the replicas have drifted apart;
+        average them so that every rank returns (and rank 0 saves) the same modules."""
+        if self.world > 1 and not self.sync_bn:
+            for b in self.D.buffers():
+                if b.is_floating_point():
+                    self.group.all_reduce(b)
+                    b /= self.world
 
     def _adam(self, grp: _FlatGroup, state):
         ops.adam_step(grp.flat.data_ptr(), grp.grad.data_ptr(), grp.exp_avg.data_ptr(), grp.exp_avg_sq.data_ptr(),

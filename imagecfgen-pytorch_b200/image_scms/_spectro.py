@@ -28,13 +28,37 @@ def spectrogram_stats(data, batch_size, **stream_kw):
     return mean, torch.sqrt(ss - mean.square()), n
 
 
+def need_reader(data, what):
+    if data is None:
+        raise NotImplementedError(
+            f"the dataset reader behind {what} is outside the B200 hot path (SURVEY.md §2); pass "
+            "data=<object with the reference's .stream(batch_size=...) protocol> (icf_b200.synth.SpectrogramStream "
+            "is a synthetic one)")
+    return data
+
+
+def shard_stream(stream, rank, world):
+    """Data parallelism: rank r keeps the batches r, r+world, ... of the (identically ordered) stream and every rank
+    runs the same number of steps (a ragged tail is dropped so that the gradient all-reduces stay matched)."""
+    if world <= 1:
+        yield from stream
+        return
+    group = []
+    for batch in stream:
+        group.append(batch)
+        if len(group) == world:
+            yield group[rank]
+            group = []
+
+
 def train_stream(E, G, D, data, attribute_names, image_shape, n_epochs, l_rate, device, batch_size, dtype=None,
-                 process_group=None, stream_kw=None, cast_attrs=None, stds_kept=3):
+                 process_group=None, stream_kw=None, cast=None, stds_kept=3, sync_bn=False):
+    """The epoch loop; E/G/D arrive initialised (the family's train() applies init_weights and, for ESRF, the warm
+    start of esrf_acoustic.py:276-284 BEFORE calling this, as the reference does)."""
     stream_kw = stream_kw or {}
-    E.apply(init_weights_std)
-    G.apply(init_weights_std)
-    D.apply(init_weights_std)
-    trainer = BiGANTrainer(E, G, D, lr=l_rate, betas=(0.5, 0.9), dtype=dtype, process_group=process_group)
+    cast = cast or (lambda t: t)
+    trainer = BiGANTrainer(E, G, D, lr=l_rate, betas=(0.5, 0.9), dtype=dtype, process_group=process_group,
+                           sync_bn=sync_bn)
     spect_mean, spect_std, n_batches = spectrogram_stats(data, batch_size, **stream_kw)
     spect_mean, spect_std = spect_mean.to(device), spect_std.to(device)
 
@@ -46,12 +70,15 @@ def train_stream(E, G, D, data, attribute_names, image_shape, n_epochs, l_rate, 
         E.train()
         G.train()
         scores = torch.zeros(8, dtype=torch.float32, device=device)
-        for batch in data.stream(batch_size=batch_size, **stream_kw):
+        steps = 0
+        for batch in shard_stream(data.stream(batch_size=batch_size, **stream_kw), trainer.rank, trainer.world):
             images = spect_to_img(batch["audio"].reshape((-1, 1, *image_shape)).float().to(device))
-            c = {k: batch[k].float().to(device) for k in attribute_names}
+            c = {k: cast(torch.clone(batch[k])).to(device) for k in attribute_names}
             trainer.step(images, c, out=scores)
-        s = scores.tolist()
-        print(s[3] / max(n_batches, 1), s[4] / max(n_batches, 1))
+            steps += 1
+        s = trainer.reduce_scores(scores).tolist()
+        print(s[3] / max(steps, 1), s[4] / max(steps, 1))
+    trainer.finish()
     optimizer_D, optimizer_E = trainer.export_optimizers()
     return E, G, D, optimizer_D, optimizer_E
 

@@ -1,11 +1,11 @@
 """Mirror of image_scms/audio_mnist.py (audio_mnist.py:173-482): spectrogram conditional BiGAN on the B200 engine.
-The dataset reader of the reference file is outside the hot path; train takes a data object with the
-reference's stream(batch_size=...) protocol instead of opening files."""
+The dataset reader of the reference file is outside the hot path; ``train`` keeps the reference's positional
+signature and takes the reader as the keyword ``data`` (an object with the reference's stream() protocol)."""
 import torch
 
 from icf_b200.modules import DiscriminatorBase, EncoderBase, GeneratorBase
 from icf_b200.trainer import BiGANTrainer, counterfactual  # noqa: F401
-from ._spectro import check_width, init_weights_std, train_stream
+from ._spectro import check_width, init_weights_std, need_reader, train_stream
 
 LATENT_DIM = 512
 IMAGE_SHAPE = (128, 128)
@@ -42,13 +42,26 @@ class Discriminator(DiscriminatorBase):
         super().__init__()
 
 
-def train(path_to_zip: str, n_epochs=200, l_rate=1e-4, device='cpu', save_images_every=2, batch_size=128, image_output_path='', data=None, dtype=None, process_group=None):
-    """Returns (E, G, D, optimizer_D, optimizer_E) like the reference.  data must provide
-    stream(batch_size=...); opening path_to_zip itself is the out-of-scope dataset reader."""
-    if data is None:
-        raise NotImplementedError(
-            "the dataset reader for path_to_zip is outside the B200 hot path; pass data=<object with .stream()>")
+def _fresh(device):
     E, G, D = Encoder().to(device), Generator().to(device), Discriminator().to(device)
+    E.apply(init_weights)
+    G.apply(init_weights)
+    D.apply(init_weights)
+    return E, G, D
+
+
+def train(path_to_zip: str,
+          n_epochs=200,
+          l_rate=1e-4,
+          device='cpu',
+          save_images_every=2,
+          batch_size=128,
+          image_output_path='',
+          *, data=None, dtype=None, process_group=None):
+    """audio_mnist.py:321-482 -> (E, G, D, optimizer_D, optimizer_E)."""
+    data = need_reader(data, "path_to_zip")
+    E, G, D = _fresh(device)
     names = [k for k in ATTRIBUTE_DIMS]
     return train_stream(E, G, D, data, names, IMAGE_SHAPE, n_epochs, l_rate, device, batch_size, dtype=dtype,
-                        process_group=process_group, stream_kw={"excluded_runs": VALIDATION_RUNS})
+                        process_group=process_group, stream_kw={"excluded_runs": VALIDATION_RUNS},
+                        cast=lambda t: t.float())          # audio_mnist.py:388

@@ -1,16 +1,15 @@
 """Mirror of image_scms/esrf_acoustic.py (esrf_acoustic.py:134-447): spectrogram conditional BiGAN on the B200 engine.
-The dataset reader of the reference file is outside the hot path; train takes a data object with the
-reference's stream(batch_size=...) protocol instead of opening files."""
+The dataset reader of the reference file is outside the hot path; ``train`` keeps the reference's positional
+signature and takes the reader as the keyword ``data`` (an object with the reference's stream() protocol)."""
 import torch
 
 from icf_b200.modules import DiscriminatorBase, EncoderBase, GeneratorBase
 from icf_b200.trainer import BiGANTrainer, counterfactual  # noqa: F401
-from ._spectro import check_width, init_weights_std, train_stream
+from ._spectro import check_width, init_weights_std, need_reader, train_stream
 
 LATENT_DIM = 512
 IMAGE_SHAPE = (512, 512)
 ATTRIBUTE_DIMS = {"closest_boat": 1, "has_boat": 2}
-
 
 
 def init_weights(layer, std=0.001):
@@ -41,18 +40,32 @@ class Discriminator(DiscriminatorBase):
         super().__init__()
 
 
-def train(station_dirs=None, n_epochs=200, l_rate=1e-4, device='cpu', save_images_every=2, image_output_path='', batch_size=64, start_model_path=None, data=None, dtype=None, process_group=None):
-    """Returns (E, G, D, optimizer_D, optimizer_E) like the reference.  data must provide
-    stream(batch_size=...); opening station_dirs itself is the out-of-scope dataset reader."""
-    if data is None:
-        raise NotImplementedError(
-            "the dataset reader for station_dirs is outside the B200 hot path; pass data=<object with .stream()>")
+def _fresh(device):
     E, G, D = Encoder().to(device), Generator().to(device), Discriminator().to(device)
+    E.apply(init_weights)
+    G.apply(init_weights)
+    D.apply(init_weights)
+    return E, G, D
+
+
+def train(path_to_wavs: str,
+          path_to_labels: str,
+          n_epochs: int = 200,
+          l_rate: float = 1e-4,
+          device: str = 'cpu',
+          save_images_every: int = 2,
+          batch_size: int = 64,
+          image_output_path: str = '',
+          validation_split=0.2,
+          start_model_path=None,
+          *, data=None, dtype=None, process_group=None):
+    """esrf_acoustic.py:263-447 -> (E, G, D, optimizer_D, optimizer_E).  ``start_model_path``: whole-module pickle
+    {'E','G','D'} (train_esrf_bigan.py:31-35) whose networks REPLACE the freshly initialised ones (:276-284)."""
+    data = need_reader(data, "path_to_wavs / path_to_labels")
+    E, G, D = _fresh(device)
     if start_model_path is not None:
-        obj = torch.load(start_model_path, map_location=device, weights_only=False)   # esrf_acoustic.py:280-284
-        E.load_state_dict(obj["E"].state_dict())
-        G.load_state_dict(obj["G"].state_dict())
-        D.load_state_dict(obj["D"].state_dict())
+        model_dict = torch.load(start_model_path, map_location=device, weights_only=False)
+        E, G, D = model_dict['E'], model_dict['G'], model_dict['D']
     names = [k for k in ATTRIBUTE_DIMS]
     return train_stream(E, G, D, data, names, IMAGE_SHAPE, n_epochs, l_rate, device, batch_size, dtype=dtype,
-                        process_group=process_group, stream_kw={})
+                        process_group=process_group, stream_kw={"mode": "train"})

@@ -238,7 +238,8 @@ int icf_bn_bwd_reduce(const void* dU, int32_t d_dtype, int32_t d_pitch, const vo
  * Backward of the fused conv epilogue (aten::leaky_relu_backward / tanh_backward / dropout backward /
  * native_batch_norm_backward / bias gradient in one pass):
  *   g      = dOut[n,pix,c]                                   (gradient w.r.t. what the consumer read)
- *   if bn: g = gamma*invstd*( g*bn_mask - sums0/M - xhat*sums1/M ),  dgamma += sums1, dbeta += sums0 (once)
+ *   if bn: g = gamma*invstd*( g*bn_mask - sums0/M - xhat*sums1/M ),  dgamma += sums1, dbeta += sums0 (once);
+ *          M = pixels (or pixels*world under SyncBN, see bn_inv_world)
  *   dPre   = g * out_mask[n,c] * act'(y)                     (act' from the saved output y)
  *   dbias[c] += sum dPre
  * ------------------------------------------------------------------------------------------------ */
@@ -260,6 +261,9 @@ typedef struct icf_actbwd_args {
   const float* bn_mask;          /* Dropout2d mask applied after the BatchNorm, or NULL */
   const float* bn_gamma; const float* bn_mean; const float* bn_invstd;
   float* bn_dgamma; float* bn_dbeta;   /* [C] += */
+  float bn_inv_world;            /* SyncBN across `world` data-parallel ranks: bn_sums were summed over all ranks (the caller
+                                    all-reduces them), so M = pixels*world and dgamma/dbeta += sums/world (the later gradient
+                                    average re-multiplies by world/world).  0 = 1 (statistics of this tensor alone). */
 } icf_actbwd_args;
 int icf_act_backward(const icf_actbwd_args* a, void* stream);
 

@@ -172,8 +172,10 @@ def param_shapes(family, net):
         return (emb_g + [("layers.0.weight", (16384, gin)), ("layers.0.bias", (16384,))]
                 + _conv_shapes("layers", gen, 5, start=3, transposed=True))
     if net == "D":
-        return (emb_ed
-                + _conv_shapes("dz", [512, 512, 512], 1)
-                + _conv_shapes("dx", [cin0] + dxc[1:], 5)
-                + _conv_shapes("dxz", [1024, 1024, 1024, 1], 1))
+        dz = _conv_shapes("dz", [512, 512, 512], 1)
+        dx = _conv_shapes("dx", [cin0] + dxc[1:], 5)
+        # registration order of the reference constructors: dz, dx, dxz (audio_mnist.py:272-297, whalecalls.py:338-365)
+        # except ESRF, which declares dx first (esrf_acoustic.py:218-241)
+        towers = dx + dz if family == "esrf_acoustic" else dz + dx
+        return emb_ed + towers + _conv_shapes("dxz", [1024, 1024, 1024, 1], 1)
     raise KeyError((family, net))

@@ -50,11 +50,18 @@ _CONTRACTIONS = ("conv", "convT", "linear", "bn")
 
 
 def run_ops(ops, sd: Dict[str, Tensor], x: Tensor, masks: Optional[List[Tensor]] = None,
-            training: bool = True, bn_update: bool = True, q=None, q_final: bool = True) -> Tensor:
+            training: bool = True, bn_update: bool = True, q=None, q_final: bool = True,
+            signs: Optional[List[Tensor]] = None) -> Tensor:
     """Execute an op table from ``oracle/arch.py`` with the semantics of the torch layers it names.
     ``q`` (optional) is applied wherever the CUDA engine stores a tensor: operands (weights), and activations
-    after [conv+activation+dropout] and after [BatchNorm+dropout]."""
+    after [conv+activation+dropout] and after [BatchNorm+dropout].
+    ``signs`` (optional, gradient parity tests): one bool tensor per LeakyReLU of the table, True where the
+    implementation under test saw a positive pre-activation.  The LeakyReLU is then evaluated as the LINEAR map
+    x * (1 | slope) selected by that mask, in forward and backward alike, so that both sides differentiate the same
+    piecewise-linear branch: a pre-activation within rounding distance of zero otherwise flips the branch and changes
+    that element's derivative by 1/slope, which no finite-precision implementation can be held to."""
     qq = q if q is not None else (lambda t: t)
+    signs = list(signs) if signs is not None else None
     n_ops = len(ops)
     for i, op in enumerate(ops):
         kind = op[0]
@@ -70,7 +77,11 @@ def run_ops(ops, sd: Dict[str, Tensor], x: Tensor, masks: Optional[List[Tensor]]
         elif kind == "unflatten":
             x = x.reshape(x.shape[0], *op[1])
         elif kind == "lrelu":
-            x = F.leaky_relu(x, op[1])
+            if signs is not None:
+                pos = signs.pop(0).reshape(x.shape)
+                x = x * torch.where(pos, torch.ones((), dtype=x.dtype), torch.full((), op[1], dtype=x.dtype))
+            else:
+                x = F.leaky_relu(x, op[1])
         elif kind == "tanh":
             x = torch.tanh(x)
         elif kind == "drop":
@@ -113,11 +124,11 @@ def dropout_sites(family: str):
     return sites
 
 
-def draw_masks(family: str, n: int, generator: Optional[torch.Generator] = None) -> List[Tensor]:
+def draw_masks(family: str, n: int, generator: Optional[torch.Generator] = None, device=None) -> List[Tensor]:
     """Masks for ONE Discriminator forward, drawn exactly like torch's Dropout2d (feature_dropout)."""
     out = []
     for p, c in dropout_sites(family):
-        out.append(torch.empty(n, c, 1, 1).bernoulli_(1 - p, generator=generator).div_(1 - p))
+        out.append(torch.empty(n, c, 1, 1, device=device).bernoulli_(1 - p, generator=generator).div_(1 - p))
     return out
 
 
@@ -187,18 +198,19 @@ def _q(q, t):
     return q(t) if q is not None else t
 
 
-def encoder_fwd(family: str, sd, X, c, q=None) -> Tensor:
+def encoder_fwd(family: str, sd, X, c, q=None, signs=None) -> Tensor:
     """Encoder.forward (mnist.py:46-56 etc.) -> (N,512,1,1)."""
-    return run_ops(FAMILIES[family]["E"], sd, _q(q, image_features(family, sd, X, c)), q=q)
+    return run_ops(FAMILIES[family]["E"], sd, _q(q, image_features(family, sd, X, c)), q=q, signs=signs)
 
 
-def generator_fwd(family: str, sd, z, c, q=None) -> Tensor:
+def generator_fwd(family: str, sd, z, c, q=None, signs=None) -> Tensor:
     """Generator.forward (mnist.py:76-86 etc.) -> (N,1,H,W)."""
-    return run_ops(FAMILIES[family]["G"], sd, _q(q, latent_features(family, sd, z, c)), q=q)
+    return run_ops(FAMILIES[family]["G"], sd, _q(q, latent_features(family, sd, z, c)), q=q, signs=signs)
 
 
-def discriminator_fwd(family: str, sd, X, z, c, masks=None, training=True, bn_update=True, q=None) -> Tensor:
-    """Discriminator.forward (mnist.py:142-154 etc.) -> logits (N,1)."""
+def discriminator_fwd(family: str, sd, X, z, c, masks=None, training=True, bn_update=True, q=None, signs=None) -> Tensor:
+    """Discriminator.forward (mnist.py:142-154 etc.) -> logits (N,1).  ``signs``: {"Dx": [...], "Dz": [...], "Dxz": [...]}."""
+    sg = signs or {}
     fam = FAMILIES[family]
     masks = list(masks) if masks is not None else None
     if training and dropout_sites(family) and masks is None:
@@ -207,9 +219,10 @@ def discriminator_fwd(family: str, sd, X, z, c, masks=None, training=True, bn_up
     zin = z.reshape(-1, fam["latent"], 1, 1)
     if q is not None and not (training and dropout_sites(family)):
         feats, zin = q(feats), q(zin)          # with input dropout the engine rounds after the mask (first op)
-    dx = run_ops(fam["Dx"], sd, feats, masks, training, bn_update, q=q)
-    dz = run_ops(fam["Dz"], sd, zin, masks, training, bn_update, q=q)
-    out = run_ops(fam["Dxz"], sd, torch.cat([dx, dz], dim=1), masks, training, bn_update, q=q, q_final=False)
+    dx = run_ops(fam["Dx"], sd, feats, masks, training, bn_update, q=q, signs=sg.get("Dx"))
+    dz = run_ops(fam["Dz"], sd, zin, masks, training, bn_update, q=q, signs=sg.get("Dz"))
+    out = run_ops(fam["Dxz"], sd, torch.cat([dx, dz], dim=1), masks, training, bn_update, q=q, q_final=False,
+                  signs=sg.get("Dxz"))
     return out.reshape(-1, 1)
 
 
@@ -299,8 +312,8 @@ class BiGANOracle:
         """
         fam = self.family
         n = images.shape[0]
-        valid = torch.ones(n, 1)
-        fake = torch.zeros(n, 1)
+        valid = torch.ones(n, 1, device=images.device)
+        fake = torch.zeros(n, 1, device=images.device)
         masks6 = [list(m) if m is not None else None for m in masks6]
         out = {}
         # Phase A — E+G update (mnist.py:224-230)

@@ -31,3 +31,17 @@ def digest_close(d, ref, tol):
     scale = max(ref["l2"], 1e-30)
     return (abs(d["l2"] - ref["l2"]) <= tol * scale and abs(d["sum"] - ref["sum"]) <= tol * max(ref["abs"], 1e-30)
             and abs(d["wsum"] - ref["wsum"]) <= tol * max(ref["abs"], 1e-30))
+
+
+def lrelu_signs(ex, tower, saved, n):
+    """Per LeakyReLU layer of one tower: bool (N,C,H,W) tensor (CPU), True where the CUDA forward's stored activation is
+    positive — the branch its backward differentiates (icf_common.cuh act_grad_from_output).  ``saved`` is the list of
+    per-layer records the engine keeps for the backward pass."""
+    out = []
+    for le, rec in zip(ex.towers[tower].layers, saved):
+        if le.spec.act != "lrelu":
+            continue
+        y = rec["y"]
+        t = y.t[:, y.off:y.off + le.Cout].float().cpu()
+        out.append((t.reshape(n, le.Hout, le.Wout, le.Cout).permute(0, 3, 1, 2) > 0).contiguous())
+    return out

@@ -15,6 +15,10 @@ from helpers import golden_inputs, rel_err, digest_close
 
 torch.set_num_threads(max(1, os.cpu_count() or 1))
 GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+# ESRF (723 M parameters): its forward is replayed in the default CPU suite; gradients and the train step of that family
+# (~15 GB of host memory, about a minute) only with ICF_HEAVY=1 — loss, Adam and loop body are family-independent and
+# pinned by the other three families
+GOLD_LIGHT = [p for p in GOLD if "esrf" not in p or os.environ.get("ICF_HEAVY")]
 
 
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
@@ -36,7 +40,7 @@ def test_forward_matches_reference(path):
         assert rel_err(cf, g["CF_out"]) < 1e-6
 
 
-@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+@pytest.mark.parametrize("path", GOLD_LIGHT, ids=[os.path.basename(p) for p in GOLD_LIGHT])
 def test_train_mode_and_grads_match_reference(path):
     g = torch.load(path, weights_only=False)
     fam, n, seed, std = g["family"], g["n"], g["seed"], g["std"]
@@ -57,7 +61,7 @@ def test_train_mode_and_grads_match_reference(path):
             assert digest_close(R.digest(got[k]), d, 1e-4), (net, k)
 
 
-@pytest.mark.parametrize("path", [p for p in GOLD if "whale" not in p], ids=lambda p: os.path.basename(p))
+@pytest.mark.parametrize("path", GOLD_LIGHT, ids=lambda p: os.path.basename(p))
 def test_train_steps_match_reference(path):
     g = torch.load(path, weights_only=False)
     if not g["step_log"]:
