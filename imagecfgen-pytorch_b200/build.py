@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "icf_b200", "libicf_b200.so")
-SOURCES = ["icf_api.cu", "icf_elementwise.cu", "icf_conv_simt.cu", "icf_conv_tc.cu", "icf_conv_ws.cu", "icf_wgrad_px8.cu", "icf_conv_sc.cu"]
+SOURCES = ["icf_api.cu", "icf_elementwise.cu", "icf_conv_simt.cu", "icf_conv_tc.cu", "icf_conv_ws.cu", "icf_wgrad_px8.cu", "icf_conv_sc.cu", "icf_finetune_scm.cu"]
 
 
 def needs_build():

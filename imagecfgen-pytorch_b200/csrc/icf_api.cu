@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 int icf_simt_conv_forward(const icf_conv_args* a, cudaStream_t st);
 int icf_simt_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st);
@@ -33,6 +34,34 @@ int check_launch(const char* what) {
 
 static std::atomic<int> g_tc{-1};
 static thread_local int g_conv_path = -1;
+
+int sm_count() {
+  static std::atomic<int> cache[SmemGuard::MAX_DEV];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= SmemGuard::MAX_DEV) return 148;
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v > 0) return v;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+  cache[dev].store(v, std::memory_order_relaxed);
+  return v;
+}
+
+static std::mutex g_smem_mu;
+SmemGuard::SmemGuard() { memset(configured, 0, sizeof(configured)); }
+int SmemGuard::ensure(const void* kernel, size_t smem, const char* what) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) dev = 0;
+  std::lock_guard<std::mutex> lock(g_smem_mu);
+  if (smem <= configured[dev]) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("%s: cannot reserve %zu B of shared memory: %s", what, smem, cudaGetErrorString(e));
+    return 1;
+  }
+  configured[dev] = smem;
+  return 0;
+}
 
 }  // namespace icf
 

@@ -21,6 +21,18 @@ int check_launch(const char* what);
   } while (0)
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// SM count of the CURRENT device (queried once per device; 148 on B200) — grid sizing never hard-codes it
+int sm_count();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize for one kernel: the attribute is per device and the library is re-entrant
+// (Python thread + torch's autograd worker thread, icf.h), so the high-water mark is kept per device under a mutex
+struct SmemGuard {
+  static constexpr int MAX_DEV = 64;
+  size_t configured[MAX_DEV];
+  SmemGuard();
+  int ensure(const void* kernel, size_t smem, const char* what);
+};
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // ---- typed load/store with fp32 math ------------------------------------------------------------

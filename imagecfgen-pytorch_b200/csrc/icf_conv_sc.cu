@@ -214,12 +214,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) conv_sc_kernel(const __grid_con
 
 template <int R, int S, int KT>
 int launch_sc(const CUtensorMap& ma, const CUtensorMap& mw, const ScParams& p, int grid, size_t smem, cudaStream_t st) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_sc_kernel<R, S, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ICF_REQUIRE(e == cudaSuccess, "scatter-form conv: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-    configured = smem;
-  }
+  static icf::SmemGuard guard;
+  if (int r = guard.ensure(reinterpret_cast<const void*>(conv_sc_kernel<R, S, KT>), smem, "scatter-form conv")) return r;
   conv_sc_kernel<R, S, KT><<<grid, SC_THREADS, smem, st>>>(ma, mw, p);
   return icf::check_launch("conv_sc");
 }
@@ -430,12 +426,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) conv_sx_kernel(const __grid_con
 
 template <int R, int S, int KT>
 int launch_sx(const CUtensorMap& ma, const CUtensorMap& mw, const ScParams& p, int grid, size_t smem, cudaStream_t st) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_sx_kernel<R, S, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ICF_REQUIRE(e == cudaSuccess, "scatter-form conv: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-    configured = smem;
-  }
+  static icf::SmemGuard guard;
+  if (int r = guard.ensure(reinterpret_cast<const void*>(conv_sx_kernel<R, S, KT>), smem, "scatter-form conv")) return r;
   conv_sx_kernel<R, S, KT><<<grid, SC_THREADS, smem, st>>>(ma, mw, p);
   return icf::check_launch("conv_sx");
 }
@@ -462,8 +454,7 @@ int icf_sc_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   p.w_bytes = (uint32_t)(8 * p.TP) * 128u;
   p.act = a->act; p.slope = a->slope; p.out_f32 = a->out_f32; p.mask_pitch = a->mask_pitch;
   p.bias = a->bias; p.mask = a->out_mask; p.dst = a->dst;
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = icf::sm_count();
   static const bool sx_off = []() { const char* e = getenv("ICF_DISABLE_SX"); return e && e[0] && e[0] != '0'; }();
   if (a->K > 1 && !sx_off && a->S - 1 <= SX_PAD) {
     // ---- shifted-operand variant ----

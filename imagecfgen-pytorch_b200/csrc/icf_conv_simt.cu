@@ -278,15 +278,10 @@ __global__ void __launch_bounds__(256) wgrad_b1_kernel(const icf_wgrad_args a) {
 template <int KS>
 int launch_wgrad_b1(const icf_wgrad_args* a, cudaStream_t st) {
   const size_t smem = ((size_t)a->H * a->W + 8 * KS * KS * 64) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    if (cudaFuncSetAttribute(wgrad_b1_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      cudaGetLastError();
-      return -1;
-    }
-    configured = smem;
-  }
-  int grid = a->N < 148 * 4 ? a->N : 148 * 4;
+  static icf::SmemGuard guard;
+  if (smem > 48 * 1024 && guard.ensure(reinterpret_cast<const void*>(wgrad_b1_kernel<KS>), smem, "single-channel wgrad")) return -1;
+  const int cap = icf::sm_count() * 4;
+  int grid = a->N < cap ? a->N : cap;
   wgrad_b1_kernel<KS><<<grid, 256, smem, st>>>(*a);
   return icf::check_launch("wgrad_b1");
 }
@@ -316,8 +311,8 @@ int icf_simt_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
   const int taps = a->R * a->S;
   const int64_t M = (int64_t)a->N * a->P * a->Q;
   const int gx = icf::cdiv(a->A, BM), gy = icf::cdiv(a->B, BN);
-  // enough splits over the pixel dimension to fill the 148 SMs a few times
-  int64_t want = (148 * 4 + (int64_t)gx * gy * taps - 1) / ((int64_t)gx * gy * taps);
+  // enough splits over the pixel dimension to fill the SMs a few times
+  int64_t want = ((int64_t)icf::sm_count() * 4 + (int64_t)gx * gy * taps - 1) / ((int64_t)gx * gy * taps);
   int64_t max_splits = (M + 255) / 256;
   int splits = (int)(want < 1 ? 1 : (want > max_splits ? max_splits : want));
   if (splits < 1) splits = 1;

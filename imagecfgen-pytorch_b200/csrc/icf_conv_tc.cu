@@ -168,6 +168,33 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
     const float* mrow = (p.mask && valid) ? p.mask + (int64_t)n * p.mask_pitch + k0 : nullptr;
     const int esize = p.out_f32 ? 4 : 2;
     uint8_t* orow = reinterpret_cast<uint8_t*>(p.dst) + (pix * p.out_pitch + k0) * esize;
+    // Dropout2d mask of this thread's row: while the main loop runs (these warps would idle on tmem_full) its lines are
+    // pulled into L2, and the 16 values of group g+1 are loaded (four 16-byte loads) while group g is in the math — a
+    // 1x1-spatial layer reads one mask row PER OUTPUT ROW; fetched on demand, 16 scalar loads per group from DRAM held the
+    // 64-CTA GEMMs at ~35 us (ncu: the epilogue's FMUL waits on them, profiles/r01_final_stall_summary.txt).
+    const int kcols = (p.K - k0) < TILE_N ? (p.K - k0) : TILE_N;
+    const bool mvec = mrow && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0) && (kcols & 15) == 0;
+    if (mrow) {
+      for (int j = 0; j < kcols; j += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(mrow + j));
+    }
+    float mk[16], mk_next[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) mk_next[j] = 1.f;
+    auto load_mask = [&](int c0) {
+      if (!mrow) return;
+      if (mvec) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(mrow + c0 + j));
+          mk_next[j] = t.x; mk_next[j + 1] = t.y; mk_next[j + 2] = t.z; mk_next[j + 3] = t.w;
+        }
+      } else {
+        const int nv = p.K - (k0 + c0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) mk_next[j] = (j < nv) ? __ldg(mrow + c0 + j) : 0.f;
+      }
+    };
+    load_mask(0);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -177,20 +204,15 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
       uint32_t v[16];
       if (n_iters > 0) {
         tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, v);
-        tmem_ld_wait();
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0u;
       }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) mk[j] = mk_next[j];
+      if (nv > 16 && c0 + 16 < TILE_N) load_mask(c0 + 16);      // next group's mask, in flight during this group's math
+      if (n_iters > 0) tmem_ld_wait();
       if (!valid) continue;
-      float mk[16];
-      if (mrow) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) mk[j] = (j < nv) ? __ldg(mrow + c0 + j) : 0.f;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) mk[j] = 1.f;
-      }
       const int nvl = nv < 16 ? nv : 16;
       int npad = (nvl + 7) & ~7;
       if (k0 + c0 + npad > p.out_pitch) npad = nvl;
@@ -364,17 +386,14 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
   if (warp == 1) tmem_dealloc_rt(tmem_base, p.tmem_cols);
 }
 
+int tc_sm_count() { return icf::sm_count(); }
+
 template <int TILE_N, int STAGES>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int64_t grid, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + TILE_N * BLOCK_K * 2) + 1024 + 256 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<TILE_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    ICF_REQUIRE(e == cudaSuccess, "tensor-core conv: cannot reserve %zu B of shared memory: %s", smem,
-                cudaGetErrorString(e));
-    configured = true;
-  }
+  // the attribute is per device and idempotent: set it on every device this thread launches on, race-free across threads
+  static icf::SmemGuard guard;
+  if (int r = guard.ensure(reinterpret_cast<const void*>(conv_tc_kernel<TILE_N, STAGES>), smem, "tensor-core conv")) return r;
   conv_tc_kernel<TILE_N, STAGES><<<(unsigned)grid, NUM_THREADS, smem, st>>>(ma, mb, p);
   return icf::check_launch("conv_tc");
 }
@@ -446,7 +465,15 @@ int icf_tc_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   p.act = a->act; p.slope = a->slope; p.out_f32 = a->out_f32; p.mask_pitch = a->mask_pitch;
   p.bias = a->bias; p.mask = a->out_mask; p.dst = a->dst;
 
-  const int tile_n = a->K > 128 ? 256 : (a->K > 64 ? 128 : (a->K > 32 ? 64 : 32));
+  int tile_n = a->K > 128 ? 256 : (a->K > 64 ? 128 : (a->K > 32 ? 64 : 32));
+  {
+    // 256-wide tiles on a grid that fills less than ~3/4 of the SMs (the 1x1-spatial 512 -> 512 layers at batch 4096: 64 CTAs
+    // on 148 SMs) leave the machine idle: twice as many 128-wide tiles (2 CTAs per SM: 96 KB ring, 128 TMEM columns) run the
+    // same work on twice the SMs.  ICF_TC_TILE=128|256 forces either (tuning aid).
+    static const int tile_env = []() { const char* e = getenv("ICF_TC_TILE"); return e ? atoi(e) : 0; }();
+    const int64_t g256 = (int64_t)p.n_classes * p.tiles_n * p.tiles_i * p.tiles_j * icf::cdiv(a->K, 256);
+    if (tile_n == 256 && (tile_env == 128 || (tile_env != 256 && g256 * 4 < (int64_t)tc_sm_count() * 3))) tile_n = 128;
+  }
   p.tiles_k = icf::cdiv(a->K, tile_n);
   const int64_t grid = (int64_t)p.n_classes * p.tiles_n * p.tiles_i * p.tiles_j * p.tiles_k;
   if (grid > 0x7FFFFFFF) return -1;
@@ -495,13 +522,8 @@ namespace {
 
 template <int TILE_N>
 int launch_wg(const CUtensorMap& ms, const CUtensorMap& mg, const WgParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<TILE_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ICF_REQUIRE(e == cudaSuccess, "tensor-core wgrad: cannot reserve %zu B of shared memory: %s", smem,
-                cudaGetErrorString(e));
-    configured = smem;
-  }
+  static icf::SmemGuard guard;
+  if (int r = guard.ensure(reinterpret_cast<const void*>(wgrad_tc_kernel<TILE_N>), smem, "tensor-core wgrad")) return r;
   wgrad_tc_kernel<TILE_N><<<grid, NUM_THREADS, smem, st>>>(ms, mg, p);
   return icf::check_launch("wgrad_tc");
 }
@@ -586,7 +608,7 @@ int wgrad_impl(const icf_wgrad_args* a, cudaStream_t st, int32_t* plan, int32_t 
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + 256;
   const int ctas_per_sm = (smem <= 110 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
   const int64_t tiles = (int64_t)p.a_tiles * p.b_tiles * p.tap_groups;
-  int64_t splits = (148 * ctas_per_sm) / tiles;          // one resident wave: never a ragged second one
+  int64_t splits = ((int64_t)icf::sm_count() * ctas_per_sm) / tiles;          // one resident wave: never a ragged second one
   if (splits > n_blocks) splits = n_blocks;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;

@@ -469,26 +469,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_ws_kernel(const __grid_con
 inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 inline int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
 
-int sm_count() {
-  static int n = []() {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
-    return v;
-  }();
-  return n;
-}
+using icf::sm_count;
 
 template <int TILE_N, int KD>
 int launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const WsParams& p, int grid, size_t smem,
               cudaStream_t st) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_ws_kernel<TILE_N, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ICF_REQUIRE(e == cudaSuccess, "row-streaming conv: cannot reserve %zu B of shared memory: %s", smem,
-                cudaGetErrorString(e));
-    configured = smem;
-  }
+  static icf::SmemGuard guard;
+  if (int r = guard.ensure(reinterpret_cast<const void*>(conv_ws_kernel<TILE_N, KD>), smem, "row-streaming conv")) return r;
   conv_ws_kernel<TILE_N, KD><<<(unsigned)grid, WS_THREADS, smem, st>>>(ma, mb, mo, p);
   return icf::check_launch("conv_ws");
 }

@@ -539,7 +539,7 @@ inline int vgrid(int C, int64_t pixels, int per_sm = 8) {
   const int cblocks = (cg + gpb - 1) / gpb;
   const int rows = VT / gpb;
   int64_t pblocks = (pixels + rows - 1) / rows;
-  const int64_t cap = (148 * per_sm + cblocks - 1) / cblocks;
+  const int64_t cap = ((int64_t)icf::sm_count() * per_sm + cblocks - 1) / cblocks;
   if (pblocks > cap) pblocks = cap;
   if (pblocks < 1) pblocks = 1;
   return (int)(pblocks * cblocks);
@@ -947,14 +947,14 @@ __global__ void fill_kernel(float* dst, float v, int64_t n) {
 
 inline int ew_grid(int64_t total, int per_thread = 1) {
   int64_t blocks = (total + (int64_t)EW_THREADS * per_thread - 1) / ((int64_t)EW_THREADS * per_thread);
-  const int64_t cap = 148 * 32;
+  const int64_t cap = (int64_t)icf::sm_count() * 32;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
 
 inline int pixel_slabs(int64_t pixels, int chan_groups) {
-  int64_t want = (148 * 8) / (chan_groups > 0 ? chan_groups : 1);
+  int64_t want = ((int64_t)icf::sm_count() * 8) / (chan_groups > 0 ? chan_groups : 1);
   int64_t maxs = (pixels + 7) / 8;
   if (want > maxs) want = maxs;
   if (want < 1) want = 1;
@@ -1104,7 +1104,7 @@ int icf_act_backward(const icf_actbwd_args* a, void* stream) {
   }
   if (a->C <= 4 && !a->bn_sums) {
     int64_t blocks = (a->pixels + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > icf::sm_count() * 8) blocks = icf::sm_count() * 8;
     act_backward_fewc_kernel<<<(unsigned)blocks, 256, 0, icf::as_stream(stream)>>>(*a);
     return icf::check_launch("act_backward_fewc");
   }

@@ -1,0 +1,180 @@
+// Kernels of the two callers either side of the hot path, all HBM-streaming:
+//   * fine-tune losses (finetune_mnist_bigan.py:68-86, finetune_whale_bigan.py:54-73): reconstruction MSE forward +
+//     gradient in one pass over the reconstruction, latent penalty mean(z^2) folded into the latent gradient;
+//   * attribute-SCM intervention (attribute_scms/graph.py:144-184): abduction + regeneration of a conditional
+//     affine -> sigmoid -> affine mechanism (the thickness -> intensity mechanism of attribute_scms/mnist.py:28-33,48),
+//     fused with the min-max rescale of mnist_gan_counterfactuals.py:57-68, and the index -> one-hot / masked swap of
+//     mnist_bigan_score.py:83-91.
+#include "icf_common.cuh"
+
+namespace {
+
+constexpr int LT = 256;
+
+// loss_out[0] += weight * mean((x - xr)^2);  dxr = weight * 2 (xr - x) / count.   x: fp32 [N][P] (target_stride = P) or one
+// image [P] broadcast over the batch (target_stride = 0); xr: [N*P][xr_pitch] (channel 0), dxr: [N*P][d_pitch] (channel 0)
+__global__ void __launch_bounds__(LT) mse_loss_kernel(const float* __restrict__ x, int64_t target_stride, const void* xr, int xr_dtype,
+                                                      int xr_pitch, int64_t n_img, int64_t P, float weight, float extra, float* loss_out,
+                                                      void* dxr, int d_dtype, int d_pitch) {
+  __shared__ float red[32];
+  const int64_t total = n_img * P;
+  const float inv = 1.f / (float)total;
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x; i < total; i += (int64_t)gridDim.x * LT) {
+    const int64_t n = i / P, pp = i - n * P;
+    const float t = x[n * target_stride + pp];
+    const float r = icf::ld_any(xr, xr_dtype, i * xr_pitch);
+    const float d = r - t;
+    s = fmaf(d, d, s);
+    if (dxr) icf::st_any(dxr, d_dtype, i * d_pitch, 2.f * weight * inv * d);
+  }
+  const float t = icf::block_sum(s, red);
+  if (threadIdx.x == 0 && loss_out) atomicAdd(loss_out, weight * (t * inv + (blockIdx.x == 0 ? extra : 0.f)));
+}
+
+// column mean of an [N][P] fp32 matrix and the mean over columns of the (biased) column variance:
+//   xbar[p] = mean_n x[n][p];   var_out[0] += mean_p( mean_n x[n][p]^2 - xbar[p]^2 )
+__global__ void __launch_bounds__(LT) col_mean_kernel(const float* __restrict__ x, int64_t N, int64_t P, float* xbar, float* var_out) {
+  __shared__ float red[32];
+  float v = 0.f;
+  for (int64_t p = (int64_t)blockIdx.x * LT + threadIdx.x; p < P; p += (int64_t)gridDim.x * LT) {
+    float s = 0.f, q = 0.f;
+    for (int64_t n = 0; n < N; ++n) {
+      const float t = x[n * P + p];
+      s += t;
+      q = fmaf(t, t, q);
+    }
+    const float m = s / (float)N;
+    xbar[p] = m;
+    v += q / (float)N - m * m;
+  }
+  const float t = icf::block_sum(v, red);
+  if (threadIdx.x == 0 && var_out) atomicAdd(var_out, t / (float)P);
+}
+
+// loss_out[0] += weight * mean(z^2);  dz[n][j] (+)= weight * 2 z / count   (z: [N][z_pitch], dz: fp32 [N][latent])
+__global__ void __launch_bounds__(LT) latent_l2_kernel(const void* z, int z_dtype, int z_pitch, int64_t N, int latent, float weight,
+                                                       float* loss_out, float* dz, int accumulate) {
+  __shared__ float red[32];
+  const int64_t total = N * latent;
+  const float inv = 1.f / (float)total;
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x; i < total; i += (int64_t)gridDim.x * LT) {
+    const int64_t n = i / latent;
+    const int j = (int)(i - n * latent);
+    const float v = icf::ld_any(z, z_dtype, n * z_pitch + j);
+    s = fmaf(v, v, s);
+    if (dz) dz[i] = (accumulate ? dz[i] : 0.f) + 2.f * weight * inv * v;
+  }
+  const float t = icf::block_sum(s, red);
+  if (threadIdx.x == 0 && loss_out) atomicAdd(loss_out, weight * t * inv);
+}
+
+// One conditional affine -> sigmoid -> affine mechanism, per sample:
+//   abduction      u = (v - lo) / span;  s = logit(u);  eps = (s - loc(p)) / scale(p)
+//   regeneration   s' = loc(p') + scale(p') * eps;      v' = lo + span * sigmoid(s')
+// (loc, log scale) = hyper-network of the parent value: out = W2 relu(W1 p + b1) + b2, hidden width H (pyro's
+// ConditionalAutoRegressiveNN for a 1-D variable with a 1-D context; H = 0: the closed form loc = a0 + a1 p,
+// log scale = a2 of the ground-truth SCM, create_train_dataset.py:42-46), log scale clamped to [clip_lo, clip_hi].
+// The counterfactual value and both parents are also written min-max scaled to [-1, 1] (mnist.py:205-209) when asked.
+__global__ void __launch_bounds__(LT) scm_affine_cf_kernel(const icf_scm_affine_args a) {
+  for (int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * LT) {
+    const float v = a.value[i], p = a.parent[i];
+    const float pc = a.parent_cf ? a.parent_cf[i] : p + a.parent_shift;
+    float loc[2], ls[2];
+    const float ctx[2] = {p, pc};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (a.hidden > 0) {
+        float o0 = a.b2[0], o1 = a.b2[1];
+        for (int h = 0; h < a.hidden; ++h) {
+          const float t = fmaxf(fmaf(a.w1[h], ctx[k], a.b1[h]), 0.f);
+          o0 = fmaf(a.w2[h], t, o0);
+          o1 = fmaf(a.w2[a.hidden + h], t, o1);
+        }
+        loc[k] = o0;
+        ls[k] = o1;
+      } else {
+        loc[k] = fmaf(a.closed[1], ctx[k], a.closed[0]);
+        ls[k] = a.closed[2];
+      }
+      ls[k] = fminf(fmaxf(ls[k], a.clip_lo), a.clip_hi);
+    }
+    float u = (v - a.lo) / a.span;
+    u = fminf(fmaxf(u, a.u_min), a.u_max);
+    const float s = logf(u) - log1pf(-u);
+    const float eps = (s - loc[0]) * expf(-ls[0]);
+    const float s2 = fmaf(expf(ls[1]), eps, loc[1]);
+    const float vcf = a.lo + a.span / (1.f + expf(-s2));
+    if (a.noise_out) a.noise_out[i] = eps;
+    if (a.value_cf) a.value_cf[i] = vcf;
+    if (a.parent_cf_out) a.parent_cf_out[i] = pc;
+    if (a.value_cf_scaled) a.value_cf_scaled[i] = 2.f * (vcf - a.v_min) / (a.v_max - a.v_min) - 1.f;
+    if (a.parent_cf_scaled) a.parent_cf_scaled[i] = 2.f * (pc - a.p_min) / (a.p_max - a.p_min) - 1.f;
+  }
+}
+
+// rows[n][:] = one_hot(idx_new[n]) where mask[n] != 0 (or mask == NULL), else the existing row stays (torch.eye(K)[idx] and
+// the masked swap of mnist_bigan_score.py:83-91, audiomnist_cf_eval.py:82-83); index dtype int32 or int64
+__global__ void __launch_bounds__(LT) onehot_swap_kernel(const void* idx, int idx64, const uint8_t* mask, int64_t n, int K, float* rows) {
+  const int64_t total = n * K;
+  for (int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x; i < total; i += (int64_t)gridDim.x * LT) {
+    const int64_t r = i / K;
+    const int k = (int)(i - r * K);
+    if (mask && !mask[r]) continue;
+    const int64_t j = idx64 ? reinterpret_cast<const int64_t*>(idx)[r] : (int64_t)reinterpret_cast<const int32_t*>(idx)[r];
+    rows[i] = (j == k) ? 1.f : 0.f;
+  }
+}
+
+inline int grid_for(int64_t total) {
+  int64_t b = (total + LT - 1) / LT;
+  const int64_t cap = (int64_t)icf::sm_count() * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+extern "C" {
+
+int icf_mse_loss(const float* x, int64_t target_stride, const void* xr, int32_t xr_dtype, int32_t xr_pitch, int64_t n_img,
+                 int64_t pixels_per_image, float weight, float extra, float* loss_out, void* dxr, int32_t d_dtype, int32_t d_pitch,
+                 void* stream) {
+  ICF_REQUIRE(x && xr && n_img > 0 && pixels_per_image > 0 && xr_pitch > 0 && (!dxr || d_pitch > 0) &&
+                  (target_stride == 0 || target_stride == pixels_per_image),
+              "icf_mse_loss: bad arguments");
+  mse_loss_kernel<<<grid_for(n_img * pixels_per_image), LT, 0, icf::as_stream(stream)>>>(
+      x, target_stride, xr, xr_dtype, xr_pitch, n_img, pixels_per_image, weight, extra, loss_out, dxr, d_dtype, d_pitch);
+  return icf::check_launch("mse_loss");
+}
+
+int icf_col_mean(const float* x, int64_t n, int64_t p, float* xbar, float* var_out, void* stream) {
+  ICF_REQUIRE(x && xbar && n > 0 && p > 0, "icf_col_mean: bad arguments");
+  col_mean_kernel<<<grid_for(p), LT, 0, icf::as_stream(stream)>>>(x, n, p, xbar, var_out);
+  return icf::check_launch("col_mean");
+}
+
+int icf_latent_l2(const void* z, int32_t z_dtype, int32_t z_pitch, int64_t n, int32_t latent, float weight, float* loss_out,
+                  float* dz, int32_t accumulate, void* stream) {
+  ICF_REQUIRE(z && n > 0 && latent > 0 && z_pitch >= latent, "icf_latent_l2: bad arguments");
+  latent_l2_kernel<<<grid_for(n * latent), LT, 0, icf::as_stream(stream)>>>(z, z_dtype, z_pitch, n, latent, weight, loss_out, dz,
+                                                                              accumulate);
+  return icf::check_launch("latent_l2");
+}
+
+int icf_scm_affine_cf(const icf_scm_affine_args* a, void* stream) {
+  ICF_REQUIRE(a && a->value && a->parent && a->n >= 0 && a->hidden >= 0 && a->span != 0.f, "icf_scm_affine_cf: bad arguments");
+  ICF_REQUIRE(a->hidden == 0 || (a->w1 && a->b1 && a->w2 && a->b2), "icf_scm_affine_cf: hyper-network weights missing");
+  if (a->n == 0) return 0;
+  scm_affine_cf_kernel<<<grid_for(a->n), LT, 0, icf::as_stream(stream)>>>(*a);
+  return icf::check_launch("scm_affine_cf");
+}
+
+int icf_onehot_swap(const void* idx, int32_t idx_is_int64, const uint8_t* mask, int64_t n, int32_t K, float* rows, void* stream) {
+  ICF_REQUIRE(idx && rows && n >= 0 && K > 0, "icf_onehot_swap: bad arguments");
+  if (n == 0) return 0;
+  onehot_swap_kernel<<<grid_for(n * K), LT, 0, icf::as_stream(stream)>>>(idx, idx_is_int64, mask, n, K, rows);
+  return icf::check_launch("onehot_swap");
+}
+
+}  // extern "C"

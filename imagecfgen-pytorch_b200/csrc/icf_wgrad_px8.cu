@@ -228,14 +228,9 @@ int icf_px8_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
     cuuint32_t box[4] = {8, (cuuint32_t)p.WP, (cuuint32_t)(p.PB + a->R - 1), 1};
     if (int r = encode_plain(&mx, a->big_t, 4, dims, str, box)) return r;
   }
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_px8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ICF_REQUIRE(e == cudaSuccess, "first-layer wgrad: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-    configured = smem;
-  }
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static icf::SmemGuard guard;
+  if (int r = guard.ensure(reinterpret_cast<const void*>(wgrad_px8_kernel), smem, "first-layer wgrad")) return r;
+  const int sms = icf::sm_count();
   const int64_t items = (int64_t)a->N * p.pblocks;
   const int grid = items < sms ? (int)items : sms;
   wgrad_px8_kernel<<<grid, PX_THREADS, smem, st>>>(mdy, mx, p);

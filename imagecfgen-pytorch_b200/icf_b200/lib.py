@@ -81,6 +81,15 @@ class ActBwdArgs(C.Structure):
                 ("bn_invstd", _vp), ("bn_dgamma", _vp), ("bn_dbeta", _vp), ("bn_inv_world", _f32)]
 
 
+class ScmAffineArgs(C.Structure):
+    _fields_ = [("n", _i64), ("hidden", _i32), ("closed", _f32 * 3), ("clip_lo", _f32), ("clip_hi", _f32),
+                ("lo", _f32), ("span", _f32), ("u_min", _f32), ("u_max", _f32), ("parent_shift", _f32),
+                ("v_min", _f32), ("v_max", _f32), ("p_min", _f32), ("p_max", _f32),
+                ("w1", _vp), ("b1", _vp), ("w2", _vp), ("b2", _vp),
+                ("value", _vp), ("parent", _vp), ("parent_cf", _vp), ("noise_out", _vp), ("value_cf", _vp),
+                ("parent_cf_out", _vp), ("value_cf_scaled", _vp), ("parent_cf_scaled", _vp)]
+
+
 _SIGS = {
     "icf_last_error": (C.c_char_p, []),
     "icf_version": (_i32, []),
@@ -112,6 +121,11 @@ _SIGS = {
     "icf_bce_logits": (_i32, [_vp, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _i32, _i32, _vp]),
     "icf_sigmoid_mean": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "icf_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "icf_mse_loss": (_i32, [_vp, _i64, _vp, _i32, _i32, _i64, _i64, _f32, _f32, _vp, _vp, _i32, _i32, _vp]),
+    "icf_col_mean": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    "icf_latent_l2": (_i32, [_vp, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _i32, _vp]),
+    "icf_scm_affine_cf": (_i32, [C.POINTER(ScmAffineArgs), _vp]),
+    "icf_onehot_swap": (_i32, [_vp, _i32, _vp, _i64, _i32, _vp, _vp]),
     "icf_cast": (_i32, [_vp, _i32, _vp, _i32, _i64, _vp]),
     "icf_fill_f32": (_i32, [_vp, _f32, _i64, _vp]),
 }

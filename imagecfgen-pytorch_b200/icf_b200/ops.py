@@ -277,3 +277,34 @@ def cast(src, src_dtype, dst, dst_dtype, n):
 
 def fill_f32(dst, value, n):
     _launch("icf_fill_f32", _l.load().icf_fill_f32, dst, value, n)
+
+
+def mse_loss(x, target_stride, xr, xr_dtype, xr_pitch, n_img, pixels, weight, extra, loss_out, dxr, d_dtype, d_pitch):
+    _launch("icf_mse_loss", _l.load().icf_mse_loss, x, target_stride, xr, xr_dtype, xr_pitch, n_img, pixels, weight, extra,
+            loss_out, dxr, d_dtype, d_pitch)
+
+
+def col_mean(x, n, p, xbar, var_out):
+    _launch("icf_col_mean", _l.load().icf_col_mean, x, n, p, xbar, var_out)
+
+
+def latent_l2(z, z_dtype, z_pitch, n, latent, weight, loss_out, dz, accumulate):
+    _launch("icf_latent_l2", _l.load().icf_latent_l2, z, z_dtype, z_pitch, n, latent, weight, loss_out, dz,
+            1 if accumulate else 0)
+
+
+def scm_affine_cf(args):
+    _launch("icf_scm_affine_cf", _l.load().icf_scm_affine_cf, C.byref(args))
+
+
+def onehot_swap(idx: torch.Tensor, mask, rows: torch.Tensor):
+    """rows (N,K) fp32 <- one_hot(idx) where mask (bool / uint8, or None = everywhere)."""
+    require_cuda(idx, rows, mask)
+    assert rows.dtype == torch.float32 and rows.is_contiguous() and idx.dtype in (torch.int32, torch.int64)
+    m = None
+    if mask is not None:
+        m = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8).contiguous()
+    n, k = rows.shape
+    _launch("icf_onehot_swap", _l.load().icf_onehot_swap, idx.contiguous().data_ptr(), 1 if idx.dtype == torch.int64 else 0,
+            ptr(m), n, k, rows.data_ptr())
+    return rows

@@ -280,6 +280,63 @@ int icf_sigmoid_mean(const void* logits, int32_t l_dtype, int32_t l_pitch, int32
                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fine-tune losses (finetune_mnist_bigan.py:68-86, finetune_audio_mnist_bigan.py:79-92, finetune_whale_bigan.py:58-73):
+ *   rec    = torch.square(x - xr).mean()         -> icf_mse_loss: loss_out[0] += weight*(mean((xr - x)^2) + extra),
+ *                                                   dxr = weight * 2 (xr - x) / count  (gradient w.r.t. the reconstruction)
+ *   latent = torch.square(codes).mean()          -> icf_latent_l2: loss_out[0] += weight*mean(z^2), dz (+)= weight*2z/count
+ * x is fp32 [n_img][pixels_per_image] (target_stride = pixels_per_image) or ONE image broadcast over the batch
+ * (target_stride = 0): finetune_whale_bigan.py:59-65 subtracts (N,256,256) from (N,1,256,256), i.e. the all-pairs mean,
+ * which equals the MSE against the batch-mean image plus the mean pixel variance (`extra`); icf_col_mean supplies both.
+ * xr / dxr address channel 0 of [n_img*pixels][pitch] tensors.
+ * ------------------------------------------------------------------------------------------------ */
+int icf_mse_loss(const float* x, int64_t target_stride, const void* xr, int32_t xr_dtype, int32_t xr_pitch, int64_t n_img,
+                 int64_t pixels_per_image, float weight, float extra, float* loss_out, void* dxr, int32_t d_dtype,
+                 int32_t d_pitch, void* stream);
+/* xbar[p] = mean_n x[n][p];  var_out[0] += mean_p(mean_n x[n][p]^2 - xbar[p]^2) */
+int icf_col_mean(const float* x, int64_t n, int64_t p, float* xbar, float* var_out, void* stream);
+int icf_latent_l2(const void* z, int32_t z_dtype, int32_t z_pitch, int64_t n, int32_t latent, float weight, float* loss_out,
+                  float* dz /* fp32 [n][latent] or NULL */, int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attribute-SCM intervention on the device — the "intervene" step between E and G of a counterfactual
+ * (attribute_scms/graph.py:144-184 sample_cf: abduct the noise of every observed variable, regenerate the
+ * descendants of the intervened ones).  One conditional affine -> sigmoid -> affine mechanism per call, the shape
+ * of MorphoMNIST's thickness -> intensity edge (attribute_scms/mnist.py:28-33,48):
+ *   abduction      u = clamp((v - lo)/span, u_min, u_max);  s = log u - log1p(-u);  eps = (s - loc(p)) * exp(-ls(p))
+ *   regeneration   s' = loc(p') + exp(ls(p')) * eps;         v' = lo + span * sigmoid(s')
+ * (loc, ls)(p) = W2 relu(W1 p + b1) + b2 with `hidden` units (pyro ConditionalAutoRegressiveNN of a 1-D variable with a
+ * 1-D context: the autoregressive mask removes the variable itself) or, hidden = 0, loc = closed[0] + closed[1]*p,
+ * ls = closed[2] (the ground-truth SCM of create_train_dataset.py:42-46: loc = 2t - 5, scale 0.5); ls is clamped to
+ * [clip_lo, clip_hi] (pyro: -5, 3).  p' = parent_cf[i], or parent[i] + parent_shift when parent_cf is NULL
+ * (mnist_gan_counterfactuals.py:63 do(thickness + 2)).  *_scaled outputs = 2 (v - min)/(max - min) - 1 (:65-68).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct icf_scm_affine_args {
+  int64_t n;
+  int32_t hidden;                /* hyper-network width, 0 = closed form */
+  float closed[3];               /* hidden == 0: loc = closed[0] + closed[1]*p, log scale = closed[2] */
+  float clip_lo, clip_hi;        /* clamp of the log scale */
+  float lo, span;                /* final affine transform of the mechanism */
+  float u_min, u_max;            /* clamp of the sigmoid pre-image (torch SigmoidTransform: tiny, 1 - eps) */
+  float parent_shift;
+  float v_min, v_max, p_min, p_max;   /* min-max statistics for the scaled outputs */
+  const float* w1; const float* b1;   /* [hidden] (context weight), [hidden] */
+  const float* w2; const float* b2;   /* [2][hidden] (loc row, log-scale row), [2] */
+  const float* value;            /* [n] observed child (intensity) */
+  const float* parent;           /* [n] observed parent (thickness) */
+  const float* parent_cf;        /* [n] counterfactual parent, or NULL */
+  float* noise_out;              /* [n] abducted noise, or NULL */
+  float* value_cf;               /* [n] raw counterfactual child, or NULL */
+  float* parent_cf_out;          /* [n] raw counterfactual parent, or NULL */
+  float* value_cf_scaled;        /* [n] or NULL */
+  float* parent_cf_scaled;       /* [n] or NULL */
+} icf_scm_affine_args;
+int icf_scm_affine_cf(const icf_scm_affine_args* a, void* stream);
+/* rows[n][:] = one_hot(idx[n]) for the rows with mask[n] != 0 (all rows when mask is NULL); other rows keep their content:
+ * torch.eye(K)[idx] and the masked attribute swap of mnist_bigan_score.py:83-91 / audiomnist_cf_eval.py:82-83. */
+int icf_onehot_swap(const void* idx, int32_t idx_is_int64, const uint8_t* mask, int64_t n, int32_t K, float* rows,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * torch.optim.Adam (mnist.py:176-179; eps 1e-8, no weight decay) over one flat fp32 buffer.
  * `state` = {step, lr, beta1, beta2, eps, grad_scale} in device memory so a captured CUDA graph can
  * be replayed: the kernel itself advances `step`.

@@ -51,7 +51,7 @@ _CONTRACTIONS = ("conv", "convT", "linear", "bn")
 
 def run_ops(ops, sd: Dict[str, Tensor], x: Tensor, masks: Optional[List[Tensor]] = None,
             training: bool = True, bn_update: bool = True, q=None, q_final: bool = True,
-            signs: Optional[List[Tensor]] = None) -> Tensor:
+            signs: Optional[List[Tensor]] = None, record: Optional[list] = None) -> Tensor:
     """Execute an op table from ``oracle/arch.py`` with the semantics of the torch layers it names.
     ``q`` (optional) is applied wherever the CUDA engine stores a tensor: operands (weights), and activations
     after [conv+activation+dropout] and after [BatchNorm+dropout].
@@ -59,21 +59,35 @@ def run_ops(ops, sd: Dict[str, Tensor], x: Tensor, masks: Optional[List[Tensor]]
     implementation under test saw a positive pre-activation.  The LeakyReLU is then evaluated as the LINEAR map
     x * (1 | slope) selected by that mask, in forward and backward alike, so that both sides differentiate the same
     piecewise-linear branch: a pre-activation within rounding distance of zero otherwise flips the branch and changes
-    that element's derivative by 1/slope, which no finite-precision implementation can be held to."""
+    that element's derivative by 1/slope, which no finite-precision implementation can be held to.
+    ``record`` (optional, gradient parity tests): every contraction / BatchNorm appends (kind, key, args, input, output)
+    with the output's gradient retained, from which ``gradient_rss`` derives the magnitude of the terms each parameter
+    gradient sums."""
     qq = q if q is not None else (lambda t: t)
     signs = list(signs) if signs is not None else None
+
+    def rec(kind, key, args, x_in, y):
+        if record is not None and y.requires_grad:
+            y.retain_grad()
+            record.append((kind, key, args, x_in.detach(), y))
     n_ops = len(ops)
     for i, op in enumerate(ops):
         kind = op[0]
         if kind == "conv":
             _, key, stride, pad = op
+            x_in = x
             x = F.conv2d(x, qq(sd[key + ".weight"]), sd[key + ".bias"], stride=stride, padding=pad)
+            rec("conv", key, (stride, pad), x_in, x)
         elif kind == "convT":
             _, key, stride, pad, opad = op
+            x_in = x
             x = F.conv_transpose2d(x, qq(sd[key + ".weight"]), sd[key + ".bias"], stride=stride,
                                    padding=pad, output_padding=opad)
+            rec("convT", key, (stride, pad, opad), x_in, x)
         elif kind == "linear":
+            x_in = x
             x = F.linear(x, qq(sd[op[1] + ".weight"]), sd[op[1] + ".bias"])
+            rec("linear", op[1], (), x_in, x)
         elif kind == "unflatten":
             x = x.reshape(x.shape[0], *op[1])
         elif kind == "lrelu":
@@ -102,6 +116,7 @@ def run_ops(ops, sd: Dict[str, Tensor], x: Tensor, masks: Optional[List[Tensor]]
                     sd[key + ".num_batches_tracked"] += 1
             else:
                 x = F.batch_norm(x, rm, rv, sd[key + ".weight"], sd[key + ".bias"], False, 0.1, 1e-5)
+            rec("bn", key, (), x, x)
         else:
             raise ValueError(kind)
         if q is not None:
@@ -198,17 +213,18 @@ def _q(q, t):
     return q(t) if q is not None else t
 
 
-def encoder_fwd(family: str, sd, X, c, q=None, signs=None) -> Tensor:
+def encoder_fwd(family: str, sd, X, c, q=None, signs=None, record=None) -> Tensor:
     """Encoder.forward (mnist.py:46-56 etc.) -> (N,512,1,1)."""
-    return run_ops(FAMILIES[family]["E"], sd, _q(q, image_features(family, sd, X, c)), q=q, signs=signs)
+    return run_ops(FAMILIES[family]["E"], sd, _q(q, image_features(family, sd, X, c)), q=q, signs=signs, record=record)
 
 
-def generator_fwd(family: str, sd, z, c, q=None, signs=None) -> Tensor:
+def generator_fwd(family: str, sd, z, c, q=None, signs=None, record=None) -> Tensor:
     """Generator.forward (mnist.py:76-86 etc.) -> (N,1,H,W)."""
-    return run_ops(FAMILIES[family]["G"], sd, _q(q, latent_features(family, sd, z, c)), q=q, signs=signs)
+    return run_ops(FAMILIES[family]["G"], sd, _q(q, latent_features(family, sd, z, c)), q=q, signs=signs, record=record)
 
 
-def discriminator_fwd(family: str, sd, X, z, c, masks=None, training=True, bn_update=True, q=None, signs=None) -> Tensor:
+def discriminator_fwd(family: str, sd, X, z, c, masks=None, training=True, bn_update=True, q=None, signs=None,
+                      record=None) -> Tensor:
     """Discriminator.forward (mnist.py:142-154 etc.) -> logits (N,1).  ``signs``: {"Dx": [...], "Dz": [...], "Dxz": [...]}."""
     sg = signs or {}
     fam = FAMILIES[family]
@@ -219,11 +235,46 @@ def discriminator_fwd(family: str, sd, X, z, c, masks=None, training=True, bn_up
     zin = z.reshape(-1, fam["latent"], 1, 1)
     if q is not None and not (training and dropout_sites(family)):
         feats, zin = q(feats), q(zin)          # with input dropout the engine rounds after the mask (first op)
-    dx = run_ops(fam["Dx"], sd, feats, masks, training, bn_update, q=q, signs=sg.get("Dx"))
-    dz = run_ops(fam["Dz"], sd, zin, masks, training, bn_update, q=q, signs=sg.get("Dz"))
+    dx = run_ops(fam["Dx"], sd, feats, masks, training, bn_update, q=q, signs=sg.get("Dx"), record=record)
+    dz = run_ops(fam["Dz"], sd, zin, masks, training, bn_update, q=q, signs=sg.get("Dz"), record=record)
     out = run_ops(fam["Dxz"], sd, torch.cat([dx, dz], dim=1), masks, training, bn_update, q=q, q_final=False,
-                  signs=sg.get("Dxz"))
+                  signs=sg.get("Dxz"), record=record)
     return out.reshape(-1, 1)
+
+
+def gradient_rss(record, sd) -> Dict[str, Tensor]:
+    """Root-sum-square of the TERMS every parameter gradient sums (after ``backward``), from the records ``run_ops`` kept:
+    a weight gradient is dW = sum_{n,p,q} dY * X, a bias gradient sum dY, BatchNorm's sum dY * xhat / sum dY.  When those
+    terms cancel (a conv bias in front of a BatchNorm, a near input-independent network at the as-shipped init scale) the
+    sum is far smaller than its terms and its relative error has no meaning; the error of ANY summation scales with the
+    terms.  Parity tests therefore bound |g - g_ref| by tol * max(|g_ref|, rss) norm-wise per tensor.  The squares are
+    pushed through the same linear operator: sum (dY*X)^2 = d/dW0 <op(X^2, W0), dY^2>."""
+    acc: Dict[str, Tensor] = {}
+
+    def add(k, v):
+        acc[k] = acc[k] + v if k in acc else v
+    for kind, key, args, x_in, y in record:
+        if y.grad is None:
+            continue
+        gy2 = y.grad.detach().double() ** 2
+        if kind == "bn":
+            g, b = sd[key + ".weight"].detach().double(), sd[key + ".bias"].detach().double()
+            xhat = (y.detach().double() - b.reshape(1, -1, 1, 1)) / g.reshape(1, -1, 1, 1)
+            add(key + ".weight", (gy2 * xhat ** 2).sum(dim=(0, 2, 3)))
+            add(key + ".bias", gy2.sum(dim=(0, 2, 3)))
+            continue
+        w0 = torch.zeros_like(sd[key + ".weight"], dtype=torch.float64).requires_grad_()
+        x2 = x_in.double() ** 2
+        if kind == "conv":
+            y2 = F.conv2d(x2, w0, None, stride=args[0], padding=args[1])
+        elif kind == "convT":
+            y2 = F.conv_transpose2d(x2, w0, None, stride=args[0], padding=args[1], output_padding=args[2])
+        else:
+            y2 = F.linear(x2, w0)
+        (gw,) = torch.autograd.grad(y2, w0, gy2)
+        add(key + ".weight", gw)
+        add(key + ".bias", gy2.sum(dim=[d for d in range(gy2.dim()) if d != 1]))
+    return {k: v.clamp_min(0).sqrt().float() for k, v in acc.items()}
 
 
 def counterfactual(family: str, E_sd, G_sd, x, c, c_cf) -> Tensor:

@@ -212,11 +212,11 @@ def test_spectrogram_train_entry_points(fam, tmp_path):
         before = {k: {n_: p.detach().clone() for n_, p in net.named_parameters()} for k, net in ck.items()}
         del ck
         res = m.train("wavs", "labels", 1, 1e-4, DEV, 2, 2, '', 0.2, path, data=data, dtype="bf16")
-        # an Adam step moves a weight by at most lr (E, G: one step; D: two); a re-initialised network (std 0.001 instead of
-        # the checkpoint's 0.02) would sit ~0.02 away
+        # an Adam step moves a weight by at most lr * (1-b1)/sqrt(1-b2) = 1.6 lr (E, G: one step; D: two); a re-initialised
+        # network (std 0.001 instead of the checkpoint's 0.02) would sit ~0.02 away
         for k, net in zip("EGD", res[:3]):
             for n_, p in net.named_parameters():
-                assert float((p.detach() - before[k][n_]).abs().max()) <= 2.02e-4, (k, n_)
+                assert float((p.detach() - before[k][n_]).abs().max()) <= 4e-4, (k, n_)
     E, G, D, optD, optE = res
     assert type(E).__module__ == f"image_scms.{fam}"
     assert int(next(iter(optD.state.values()))["step"]) == 2 and int(next(iter(optE.state.values()))["step"]) == 1

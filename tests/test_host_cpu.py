@@ -313,3 +313,125 @@ def test_two_rank_gloo_gradient_buckets(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("OK" in o for o in outs), outs
+
+
+_DP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from icf_b200 import dp
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+g = dp.Group(dist.group.WORLD)
+assert (g.rank, g.world) == (rank, world)
+# replicas: every rank ends with rank 0's parameters and buffers
+torch.manual_seed(100 + rank)
+flat, buf, nbt = torch.randn(1000), torch.randn(7), torch.tensor(rank, dtype=torch.long)
+g.broadcast_state([flat, buf, nbt])
+torch.manual_seed(100)
+assert torch.equal(flat, torch.randn(1000)) and torch.equal(buf, torch.randn(7)) and int(nbt) == 0
+# rank-offset random streams: rank 0 keeps the default stream, the others leave it
+torch.manual_seed(5)
+g.seed_offset("cpu")
+mine = torch.rand(4)
+torch.manual_seed(5)
+base = torch.rand(4)
+assert torch.equal(mine, base) == (rank == 0)
+# sharded epoch: same step count on every rank, disjoint batches, drawn by rank 0
+import numpy as np
+np.random.seed(1000 + rank)
+batches = dp.shard_permutation(103, 8, g)
+assert len(batches) == 103 // 16 and all(len(b) == 8 for b in batches)
+mine = torch.cat(batches)
+both = [torch.empty_like(mine) for _ in range(world)]
+dist.all_gather(both, mine)
+allidx = torch.cat(both)
+assert allidx.unique().numel() == allidx.numel() == 96
+# SyncBN statistics: sum / sum of squares of the shards = those of the whole batch
+torch.manual_seed(7)
+x = torch.randn(2 * 6, 5, 3, 3)
+shard = x[rank * 6:(rank + 1) * 6]
+stats = torch.cat([shard.sum(dim=(0, 2, 3)), shard.square().sum(dim=(0, 2, 3))])
+dp.sync_stats(g, stats)
+cnt = 6 * 9 * world
+mean, var = stats[:5] / cnt, stats[5:] / cnt - (stats[:5] / cnt) ** 2
+assert torch.allclose(mean, x.mean(dim=(0, 2, 3)), atol=1e-5) and torch.allclose(var, x.var(dim=(0, 2, 3), unbiased=False), atol=1e-5)
+dist.barrier()
+print("OK", flush=True)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_data_parallel_plumbing(tmp_path):
+    """icf_b200.dp with world_size 2 over gloo: replica broadcast, rank-offset RNG, sharded permutation, SyncBN statistics."""
+    script = tmp_path / "dpw.py"
+    script.write_text(_DP_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29617", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), os.path.join(ROOT, "imagecfgen-pytorch_b200")],
+                              env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("OK" in o for o in outs), outs
+
+
+def test_gradient_buckets_and_single_rank_sharding():
+    from icf_b200 import dp
+    offs = [0, 10, 30, 31, 100, 260]
+    r = dp.bucket_ranges(offs, 64)
+    assert r[0][1] == 260 and r[-1][0] == 0                       # from the end of the buffer to its start
+    assert all(a[0] == b[1] for a, b in zip(r, r[1:]))            # contiguous, no gaps
+    assert all(hi - lo >= 64 for lo, hi in r[:-1]) and all(lo in offs and hi in offs for lo, hi in r)
+    g = dp.Group(None)
+    import numpy as np
+    np.random.seed(3)
+    b = dp.shard_permutation(10, 4, g)
+    assert [len(t) for t in b] == [4, 4, 2] and sorted(torch.cat(b).tolist()) == list(range(10))    # batchify semantics
+
+
+def test_train_signatures_match_the_reference():
+    """Positional parameters of the four train() entry points (mnist.py:157-167, audio_mnist.py:321-327, whalecalls.py:390-399,
+    esrf_acoustic.py:263-272): a reference caller (train_esrf_bigan.py:24 passes path_to_wavs, path_to_labels positionally)
+    must bind the same way; our additions are keyword-only."""
+    import importlib
+    import inspect
+    want = {"mnist": ["x_train", "a_train", "x_test", "a_test", "n_epochs", "l_rate", "device", "save_images_every",
+                      "image_output_path", "batch_size", "d_updates_per_g_update"],
+            "audio_mnist": ["path_to_zip", "n_epochs", "l_rate", "device", "save_images_every", "batch_size", "image_output_path"],
+            "whalecalls": ["nocall_directory", "gunshot_directory", "upcall_directory", "n_epochs", "l_rate", "device",
+                           "save_images_every", "batch_size", "image_output_path", "filter_length"],
+            "esrf_acoustic": ["path_to_wavs", "path_to_labels", "n_epochs", "l_rate", "device", "save_images_every", "batch_size",
+                              "image_output_path", "validation_split", "start_model_path"]}
+    for fam, names in want.items():
+        sig = inspect.signature(importlib.import_module(f"image_scms.{fam}").train)
+        pos = [p.name for p in sig.parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]
+        assert pos == names, (fam, pos)
+        assert all(p.kind == p.KEYWORD_ONLY for p in sig.parameters.values() if p.name not in names)
+
+
+class _TinyNet(torch.nn.Module):
+    def __init__(self, v):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.full((3,), float(v)))
+
+
+def test_esrf_warm_start_is_what_gets_trained(monkeypatch, tmp_path):
+    """esrf_acoustic.py:276-284: init_weights first, THEN the networks of start_model_path replace E/G/D — the loop must
+    receive the checkpoint's modules untouched (round 1 re-initialised them inside the loop)."""
+    from image_scms import esrf_acoustic as m
+    Tiny = _TinyNet
+    path = str(tmp_path / "ck.tar")
+    torch.save({"E": Tiny(1), "G": Tiny(2), "D": Tiny(3)}, path)
+    seen = {}
+
+    def fake_loop(E, G, D, *a, **k):
+        seen["nets"] = (E, G, D)
+        return E, G, D, None, None
+
+    monkeypatch.setattr(m, "_fresh", lambda device: (Tiny(0), Tiny(0), Tiny(0)))
+    monkeypatch.setattr(m, "train_stream", fake_loop)
+    E, G, D, _, _ = m.train("wavs", "labels", 1, 1e-4, "cpu", 2, 2, "", 0.2, path, data=object())
+    assert [float(n.w[0]) for n in seen["nets"]] == [1.0, 2.0, 3.0]
+    m.train("wavs", "labels", 1, data=object())
+    assert [float(n.w[0]) for n in seen["nets"]] == [0.0, 0.0, 0.0]
+    with pytest.raises(NotImplementedError, match="dataset reader"):
+        m.train("wavs", "labels")
