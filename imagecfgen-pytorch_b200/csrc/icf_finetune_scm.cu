@@ -14,7 +14,7 @@ constexpr int LT = 256;
 // loss_out[0] += weight * mean((x - xr)^2);  dxr = weight * 2 (xr - x) / count.   x: fp32 [N][P] (target_stride = P) or one
 // image [P] broadcast over the batch (target_stride = 0); xr: [N*P][xr_pitch] (channel 0), dxr: [N*P][d_pitch] (channel 0)
 __global__ void __launch_bounds__(LT) mse_loss_kernel(const float* __restrict__ x, int64_t target_stride, const void* xr, int xr_dtype,
-                                                      int xr_pitch, int64_t n_img, int64_t P, float weight, float extra, float* loss_out,
+                                                      int xr_pitch, int64_t n_img, int64_t P, float weight, const float* extra, float* loss_out,
                                                       void* dxr, int d_dtype, int d_pitch) {
   __shared__ float red[32];
   const int64_t total = n_img * P;
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(LT) mse_loss_kernel(const float* __restrict__ 
     if (dxr) icf::st_any(dxr, d_dtype, i * d_pitch, 2.f * weight * inv * d);
   }
   const float t = icf::block_sum(s, red);
-  if (threadIdx.x == 0 && loss_out) atomicAdd(loss_out, weight * (t * inv + (blockIdx.x == 0 ? extra : 0.f)));
+  if (threadIdx.x == 0 && loss_out) atomicAdd(loss_out, weight * (t * inv + ((blockIdx.x == 0 && extra) ? extra[0] : 0.f)));
 }
 
 // column mean of an [N][P] fp32 matrix and the mean over columns of the (biased) column variance:
@@ -138,7 +138,7 @@ inline int grid_for(int64_t total) {
 extern "C" {
 
 int icf_mse_loss(const float* x, int64_t target_stride, const void* xr, int32_t xr_dtype, int32_t xr_pitch, int64_t n_img,
-                 int64_t pixels_per_image, float weight, float extra, float* loss_out, void* dxr, int32_t d_dtype, int32_t d_pitch,
+                 int64_t pixels_per_image, float weight, const float* extra, float* loss_out, void* dxr, int32_t d_dtype, int32_t d_pitch,
                  void* stream) {
   ICF_REQUIRE(x && xr && n_img > 0 && pixels_per_image > 0 && xr_pitch > 0 && (!dxr || d_pitch > 0) &&
                   (target_stride == 0 || target_stride == pixels_per_image),

@@ -121,7 +121,7 @@ _SIGS = {
     "icf_bce_logits": (_i32, [_vp, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _i32, _i32, _vp]),
     "icf_sigmoid_mean": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "icf_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
-    "icf_mse_loss": (_i32, [_vp, _i64, _vp, _i32, _i32, _i64, _i64, _f32, _f32, _vp, _vp, _i32, _i32, _vp]),
+    "icf_mse_loss": (_i32, [_vp, _i64, _vp, _i32, _i32, _i64, _i64, _f32, _vp, _vp, _vp, _i32, _i32, _vp]),
     "icf_col_mean": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "icf_latent_l2": (_i32, [_vp, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _i32, _vp]),
     "icf_scm_affine_cf": (_i32, [C.POINTER(ScmAffineArgs), _vp]),
@@ -135,6 +135,21 @@ EXPORTED_SYMBOLS = tuple(_SIGS)
 _lib = None
 
 
+def _check_fresh():
+    """Refuse a library that was not built from the sources of this tree (build.py stores their fingerprint next to it)."""
+    build_py = os.path.join(os.path.dirname(_HERE), "build.py")
+    if os.environ.get("ICF_SKIP_FRESH_CHECK") or not os.path.exists(build_py):
+        return
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("icf_build", build_py)
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    if b.built_hash() != b.source_hash():
+        raise RuntimeError(
+            f"{LIB_PATH} is stale: it was not built from the current csrc/ + include/icf.h "
+            "(run `python imagecfgen-pytorch_b200/build.py` or __graft_entry__.build()).")
+
+
 def load():
     """Load (once) and return the ctypes handle; raises if the extension has not been built."""
     global _lib
@@ -144,6 +159,7 @@ def load():
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python imagecfgen-pytorch_b200/build.py` "
             "(or __graft_entry__.build()). The hot path has no CPU / eager fallback.")
+    _check_fresh()
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in _SIGS.items():
         fn = getattr(lib, name)

@@ -281,16 +281,17 @@ int icf_sigmoid_mean(const void* logits, int32_t l_dtype, int32_t l_pitch, int32
 
 /* ------------------------------------------------------------------------------------------------
  * Fine-tune losses (finetune_mnist_bigan.py:68-86, finetune_audio_mnist_bigan.py:79-92, finetune_whale_bigan.py:58-73):
- *   rec    = torch.square(x - xr).mean()         -> icf_mse_loss: loss_out[0] += weight*(mean((xr - x)^2) + extra),
+ *   rec    = torch.square(x - xr).mean()         -> icf_mse_loss: loss_out[0] += weight*(mean((xr - x)^2) + extra[0]),
  *                                                   dxr = weight * 2 (xr - x) / count  (gradient w.r.t. the reconstruction)
  *   latent = torch.square(codes).mean()          -> icf_latent_l2: loss_out[0] += weight*mean(z^2), dz (+)= weight*2z/count
  * x is fp32 [n_img][pixels_per_image] (target_stride = pixels_per_image) or ONE image broadcast over the batch
  * (target_stride = 0): finetune_whale_bigan.py:59-65 subtracts (N,256,256) from (N,1,256,256), i.e. the all-pairs mean,
- * which equals the MSE against the batch-mean image plus the mean pixel variance (`extra`); icf_col_mean supplies both.
+ * which equals the MSE against the batch-mean image plus the mean pixel variance (`extra`, a device scalar or NULL);
+ * icf_col_mean supplies both.
  * xr / dxr address channel 0 of [n_img*pixels][pitch] tensors.
  * ------------------------------------------------------------------------------------------------ */
 int icf_mse_loss(const float* x, int64_t target_stride, const void* xr, int32_t xr_dtype, int32_t xr_pitch, int64_t n_img,
-                 int64_t pixels_per_image, float weight, float extra, float* loss_out, void* dxr, int32_t d_dtype,
+                 int64_t pixels_per_image, float weight, const float* extra, float* loss_out, void* dxr, int32_t d_dtype,
                  int32_t d_pitch, void* stream);
 /* xbar[p] = mean_n x[n][p];  var_out[0] += mean_p(mean_n x[n][p]^2 - xbar[p]^2) */
 int icf_col_mean(const float* x, int64_t n, int64_t p, float* xbar, float* var_out, void* stream);

@@ -1,0 +1,198 @@
+"""SURVEY.md §8(f) rows next to the hot path, held to their oracles: N1 the fused encoder fine-tune step
+(finetune_*_bigan.py), N2 the device-side attribute intervention + counterfactual pipeline (attribute_scms/graph.py:144-184,
+mnist_gan_counterfactuals.py:57-73), a9 the AdversariallyLearnedInference wrapper, a15 the unfused fine-tune through autograd."""
+import math
+
+import pytest
+import torch
+
+from helpers import golden_inputs, rel_err
+from oracle import bigan_ref as R
+from oracle import scm_ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def family_module(fam):
+    import importlib
+    return importlib.import_module(f"image_scms.{fam}")
+
+
+def build(fam, seed, std, dtype, which="EG"):
+    m = family_module(fam)
+    nets = {}
+    for k, cls in (("E", m.Encoder), ("G", m.Generator), ("D", m.Discriminator)):
+        if k not in which:
+            continue
+        net = cls()
+        net.load_state_dict(R.synth_state_dict(fam, k, seed, std))
+        nets[k] = net.to(DEV).set_compute_dtype(dtype)
+    return nets
+
+
+def to_dev(c):
+    return {k: v.to(DEV) for k, v in c.items()}
+
+
+def _oracle_finetune(fam, seed, std, images, c, steps, metric="mse", all_pairs=False):
+    sdE = {k: (v.clone().float().requires_grad_(True) if v.is_floating_point() else v.clone())
+           for k, v in R.synth_state_dict(fam, "E", seed, std).items()}
+    sdG = R.synth_state_dict(fam, "G", seed, std)
+    adam = R.AdamState([v for v in sdE.values() if v.requires_grad], lr=1e-5, betas=(0.9, 0.999))
+    log = [scm_ref.finetune_step(fam, sdE, sdG, adam, images, c, metric, all_pairs) for _ in range(steps)]
+    return log, sdE
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", [("mnist", 64, 16, 0.05, "mse", False), ("mnist", 16, 17, 0.05, "ssim", False),
+                                  ("audio_mnist", 2, 13, 0.02, "mse", False), ("whalecalls", 2, 14, 0.02, "mse", True)],
+                         ids=lambda c: f"{c[0]}-{c[4]}{'-allpairs' if c[5] else ''}")
+def test_fused_finetune_step_vs_oracle(case, dtype):
+    """finetune_mnist_bigan.py:68-86 (MSE and 1-SSIM), finetune_audio_mnist_bigan.py:79-92, finetune_whale_bigan.py:58-73 (its
+    all-pairs broadcast included): reconstruction and latent losses of two consecutive steps and E's parameters afterwards."""
+    from icf_b200.finetune import EncoderFineTuner
+    fam, n, seed, std, metric, all_pairs = case
+    tol = 1e-3 if dtype == "fp32" else 2e-2
+    images, c, _, _ = golden_inputs(fam, n, seed)
+    want, sdE = _oracle_finetune(fam, seed, std, images, c, 2, metric, all_pairs)
+    nets = build(fam, seed, std, dtype)
+    G_before = {k: v.clone() for k, v in nets["G"].state_dict().items()}
+    ft = EncoderFineTuner(nets["E"], nets["G"], lr=1e-5, metric=metric, all_pairs=all_pairs)
+    x = images.to(DEV)
+    x_in = x.reshape(n, *x.shape[-2:]) if all_pairs else x          # the whale script feeds (N,H,W)
+    got = []
+    for _ in range(2):
+        out = ft.step(x_in, to_dev(c))
+        got.append(out.tolist())
+    print(fam, metric, dtype, got, want)
+    for g_, w_ in zip(got, want):
+        for a, b in zip(g_, w_):
+            assert abs(a - b) <= tol * max(abs(b), 1e-3), (got, want)
+    if dtype == "fp32":
+        for k, p in nets["E"].named_parameters():
+            assert rel_err(p, sdE[k]) < 1e-3, k
+    assert all(torch.equal(v, G_before[k]) for k, v in nets["G"].state_dict().items())       # G is frozen
+    opt = ft.export_optimizer()
+    assert int(next(iter(opt.state.values()))["step"]) == 2
+
+
+def test_unfused_finetune_through_autograd_matches():
+    """The scripts' own formulation — E, G as modules, torch autograd, torch.optim.Adam over E — on the engine (row a15)."""
+    fam, n, seed, std = "mnist", 16, 18, 0.05
+    images, c, _, _ = golden_inputs(fam, n, seed)
+    want, sdE = _oracle_finetune(fam, seed, std, images, c, 1)
+    nets = build(fam, seed, std, "fp32")
+    E, G = nets["E"], nets["G"]
+    E.train()
+    G.eval()
+    opt = torch.optim.Adam(E.parameters(), lr=1e-5)
+    x, cd = images.to(DEV), to_dev(c)
+    opt.zero_grad()
+    codes = E(x, cd)
+    xr = G(codes, cd)
+    rec = torch.square(x - xr).mean()
+    latent = torch.square(codes).mean()
+    (rec + latent).backward()
+    opt.step()
+    assert abs(float(rec) - want[0][0]) < 1e-3 * want[0][0] and abs(float(latent) - want[0][1]) < 1e-3 * want[0][1]
+    for k, p in E.named_parameters():
+        assert rel_err(p, sdE[k]) < 1e-3, k
+
+
+def test_ali_wrapper_and_losses():
+    """training_utils.AdversariallyLearnedInference / log_loss / rec_loss (training_utils.py:49-111) over the engine modules."""
+    from image_scms.training_utils import AdversariallyLearnedInference, log_loss, ssim
+    fam, n, seed, std = "mnist", 8, 19, 0.05
+    images, c, z, _ = golden_inputs(fam, n, seed)
+    nets = build(fam, seed, std, "fp32", "EGD")
+    for m in nets.values():
+        m.eval()
+    ali = AdversariallyLearnedInference(nets["E"], nets["G"], nets["D"])
+    x, zz, cd = images.to(DEV), z.to(DEV), to_dev(c)
+    sds = {k: R.synth_state_dict(fam, k, seed, std) for k in "EGD"}
+    with torch.no_grad():
+        dg, de = ali(x, zz, a=cd)
+        ex = R.encoder_fwd(fam, sds["E"], images, c)
+        gz = R.generator_fwd(fam, sds["G"], z, c)
+        rdg = R.discriminator_fwd(fam, sds["D"], gz, z, c, training=False)
+        rde = R.discriminator_fwd(fam, sds["D"], images, ex, c, training=False)
+        assert rel_err(dg, rdg) < 1e-3 and rel_err(de, rde) < 1e-3
+        s0, s1 = torch.sigmoid(dg), torch.sigmoid(de)
+        want = -torch.mean(torch.log(torch.sigmoid(rde) + 1e-6) + torch.log(1 - torch.sigmoid(rdg) + 1e-6))
+        assert abs(float(log_loss(s0, s1)) - float(want)) < 1e-3 * abs(float(want))
+        rec = R.generator_fwd(fam, sds["G"], ex, c)
+        for metric, ref in (("mse", torch.square(images - rec).mean()), ("ssim", 1 - ssim(images, rec, data_range=1.0))):
+            got = ali.rec_loss(x, a=cd, metric=metric)
+            assert abs(float(got) - float(ref)) < 1e-3 * abs(float(ref)), metric
+        with pytest.raises(ValueError, match="Invalid metric"):
+            ali.rec_loss(x, a=cd, metric="psnr")
+
+
+def test_scm_intervention_kernel_vs_oracle():
+    """icf_scm_affine_cf against the float64 restatement (closed form of the dataset SCM, and a hyper-network mechanism);
+    icf_onehot_swap bit-exact against torch.eye(K)[idx] + masked assignment."""
+    from icf_b200.scm import AffineSigmoidMechanism, onehot_swap
+    g = torch.Generator().manual_seed(5)
+    n = 100003
+    t = 0.5 + torch.rand(n, 1, generator=g) * 4
+    eps = torch.randn(n, 1, generator=g)
+    inten = 191 * torch.sigmoid(0.5 * eps + 2 * t - 5) + 64
+    mech = AffineSigmoidMechanism.morphomnist_ground_truth(DEV)
+    r = mech.counterfactual(inten.to(DEV), t.to(DEV), parent_shift=2.0, value_stats=(64.0, 255.0), parent_stats=(0.5, 6.5),
+                            want_noise=True)
+    want, e_hat = scm_ref.affine_sigmoid_cf(inten, t, t + 2, 64.0, 191.0, (-5.0, 2.0, math.log(0.5)))
+    ok = (0.5 * eps + 2 * t - 5).abs().reshape(-1) < 9           # un-saturated sigmoid: the noise is recoverable in fp32
+    assert rel_err(r["value_cf"].reshape(-1)[ok.to(DEV)], want[ok]) < 1e-5
+    assert float((r["noise"].cpu().reshape(-1)[ok] - e_hat[ok].float()).abs().max()) < 2e-2     # logit() amplifies fp32 rounding near 0/1
+    assert torch.allclose(r["parent_cf"].cpu(), t + 2)
+    assert torch.allclose(r["value_cf_scaled"].cpu().reshape(-1), (2 * (r["value_cf"].cpu().reshape(-1) - 64) / 191 - 1), atol=1e-6)
+    assert torch.allclose(r["parent_cf_scaled"].cpu(), 2 * (t + 2 - 0.5) / 6 - 1, atol=1e-6)
+    hyper = {"w1": 0.3 * torch.randn(10, generator=g), "b1": 0.3 * torch.randn(10, generator=g),
+             "w2": 0.3 * torch.randn(2, 10, generator=g), "b2": 0.3 * torch.randn(2, generator=g)}
+    t_cf = 0.5 + torch.rand(n, 1, generator=g) * 4
+    mech2 = AffineSigmoidMechanism(64.0, 191.0, hyper=hyper, device=DEV)
+    r2 = mech2.counterfactual(inten.to(DEV), t.to(DEV), parent_cf=t_cf.to(DEV))
+    want2, _ = scm_ref.affine_sigmoid_cf(inten, t, t_cf, 64.0, 191.0, hyper=hyper)
+    assert rel_err(r2["value_cf"].reshape(-1)[ok.to(DEV)], want2[ok]) < 1e-4
+    # categorical swap (mnist_bigan_score.py:83-91): bit-exact
+    K = 10
+    old = torch.randint(0, K, (n,), generator=g)
+    new = torch.randint(0, K, (n,), generator=g)
+    mask = torch.rand(n, generator=g) < 0.5
+    onehot = torch.eye(K)[old]
+    ref = onehot.clone()
+    ref[mask] = torch.eye(K)[new[mask]]
+    assert torch.equal(onehot_swap(onehot.to(DEV), new.to(DEV), mask.to(DEV)).cpu(), ref)
+    assert torch.equal(onehot_swap(onehot.to(DEV), new.to(DEV).int()).cpu(), torch.eye(K)[new])
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_counterfactual_pipeline_device_resident(dtype):
+    """encode -> do(thickness + 2) with intensity regenerated from its abducted noise -> rescale -> decode, all on the device
+    (mnist_gan_counterfactuals.py:57-73), eager and as one captured CUDA graph, against the oracle fed the host-side
+    intervention of the synthetic pipeline."""
+    from icf_b200 import synth
+    from icf_b200.scm import CounterfactualPipeline
+    fam, n, seed, std = "mnist", 256, 23, 0.05
+    tol = 1e-3 if dtype == "fp32" else 2e-2
+    x, a, _ = synth.mnist_batch(n, seed)
+    stats = synth.mnist_attr_stats()
+    images, c = synth.mnist_scale(x, a, stats)
+    _, c_cf = synth.mnist_scale(x, synth.intervene_mnist(a, 2.0), stats)
+    sds = {k: R.synth_state_dict(fam, k, seed, std) for k in "EG"}
+    ref = R.counterfactual(fam, sds["E"], sds["G"], images, c, c_cf)
+    nets = build(fam, seed, std, dtype)
+    pipe = CounterfactualPipeline(nets["E"], nets["G"], {k: (float(v[0]), float(v[1])) for k, v in stats.items()})
+    a_dev = to_dev(a)
+    _, ccf_dev = pipe.attributes(a_dev, 2.0)
+    for k in ("thickness", "intensity"):
+        assert torch.allclose(ccf_dev[k].cpu(), c_cf[k], atol=2e-4), k           # fp32 logit/sigmoid round trip
+    out = pipe(images.to(DEV), a_dev, 2.0)
+    assert rel_err(out, ref) < tol
+    pipe.capture(images.to(DEV), a_dev, 2.0)
+    x2, a2, _ = synth.mnist_batch(n, seed + 1)
+    im2, c2 = synth.mnist_scale(x2, a2, stats)
+    _, c2_cf = synth.mnist_scale(x2, synth.intervene_mnist(a2, 2.0), stats)
+    out2 = pipe.replay(im2.to(DEV), to_dev(a2))
+    assert rel_err(out2, R.counterfactual(fam, sds["E"], sds["G"], im2, c2, c2_cf)) < tol

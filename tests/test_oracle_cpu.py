@@ -115,3 +115,39 @@ def test_np_batchnorm_bce_adam_nearest():
     idx = F.interpolate(torch.arange(16.).reshape(1, 1, 1, 16), size=(1, 28), mode="nearest").long().flatten()
     assert (np_ops.nearest_index(28, 16) == idx.numpy()).all()
     assert (np_ops.nearest_index(128, 16) == np.arange(128) // 8).all()
+
+
+# ---- attribute-SCM intervention (N2) pinned to the reference's data-generating SCM ------------------------------
+def test_scm_closed_form_matches_the_dataset_scm():
+    """create_train_dataset.py:42-46: intensity = 191*sigmoid(0.5*eps + 2t - 5) + 64.  Abduction recovers eps, regeneration
+    with the factual thickness returns the observed intensity, with thickness + 2 it equals generate_i(t + 2, noise=eps)."""
+    from oracle import scm_ref
+    g = torch.Generator().manual_seed(3)
+    t = 0.5 + torch.rand(500, 1, generator=g, dtype=torch.float64) * 4
+    eps = torch.randn(500, 1, generator=g, dtype=torch.float64)
+    inten = 191 * torch.sigmoid(0.5 * eps + 2 * t - 5) + 64
+    closed = (-5.0, 2.0, math.log(0.5))
+    v_same, e_hat = scm_ref.affine_sigmoid_cf(inten, t, t, 64.0, 191.0, closed)
+    assert torch.allclose(e_hat, eps.reshape(-1), atol=1e-6) and torch.allclose(v_same, inten.reshape(-1), atol=1e-8)
+    v_cf, _ = scm_ref.affine_sigmoid_cf(inten, t, t + 2, 64.0, 191.0, closed)
+    assert torch.allclose(v_cf, (191 * torch.sigmoid(0.5 * eps + 2 * (t + 2) - 5) + 64).reshape(-1), atol=1e-8)
+    # the synthetic pipeline's own intervention (icf_b200.synth.intervene_mnist) is the same map
+    from icf_b200 import synth
+    a = {"thickness": t.float(), "intensity": inten.float()}
+    assert torch.allclose(synth.intervene_mnist(a)["intensity"].double().reshape(-1), v_cf, rtol=1e-4)
+
+
+def test_scm_hyper_network_form_is_invertible():
+    from oracle import scm_ref
+    g = torch.Generator().manual_seed(4)
+    hyper = {"w1": 0.3 * torch.randn(10, generator=g), "b1": 0.3 * torch.randn(10, generator=g),
+             "w2": 0.3 * torch.randn(2, 10, generator=g), "b2": 0.3 * torch.randn(2, generator=g)}
+    t = 0.5 + torch.rand(200, generator=g) * 4
+    eps = torch.randn(200, generator=g, dtype=torch.float64)
+    loc, ls = scm_ref.hyper_net(t.double(), {k: v.double() for k, v in hyper.items()}, None)
+    s = loc + torch.exp(ls) * eps
+    inten = 64 + 191 * torch.sigmoid(s)
+    v_same, e_hat = scm_ref.affine_sigmoid_cf(inten, t, t, 64.0, 191.0, hyper=hyper)
+    ok = s.abs() < 10          # beyond that the sigmoid saturates and SigmoidTransform's clamp (1 - eps) discards the noise
+    assert int(ok.sum()) > 150
+    assert torch.allclose(e_hat[ok], eps[ok], atol=1e-4) and torch.allclose(v_same, inten, atol=1e-4)
