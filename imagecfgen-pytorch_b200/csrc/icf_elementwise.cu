@@ -39,60 +39,76 @@ __global__ void argmax_rows_kernel(const void* x, int dt, int n, int k, int32_t*
 
 // ------------------------------------------------------------------------------------------------
 // image feature stack: [x | tanh(upsample16(emb[idx])) ... | const planes ...] * mask, NHWC pitch 8
-// one thread per pixel writes the whole (<= 8 channel) vector
+// A block works on one sample at a time: the sample's 16x16 attribute planes (tanh applied, Dropout2d mask folded in) and
+// its constant planes are staged in shared memory once (256 tanh per plane instead of one per pixel), then the threads
+// stream the pixels: one 4-byte read of the image and one 16-byte store of the (<= 8 channel) vector per pixel.
+// grid = (samples, pixel slabs): big images (512x512) are split so that a small batch still fills the machine.
 // ------------------------------------------------------------------------------------------------
-__global__ void imgfeat_fwd_kernel(const icf_imgfeat_args a) {
+__global__ void __launch_bounds__(EW_THREADS) imgfeat_fwd_kernel(const icf_imgfeat_args a) {
+  __shared__ float plane[ICF_MAX_PLANES - 1][256];
+  __shared__ float cst[8], mk0;
+  __shared__ uint8_t cxs[640];                                          // cell column of every padded x (W + 2 pad <= 640)
   const int Hp = a.H + 2 * a.pad, Wp = a.W + 2 * a.pad;
-  const int64_t total = (int64_t)a.N * Hp * Wp;
-  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // padded output pixel
-  if (o >= total) return;
-  const int hwp = Hp * Wp;
-  const int n = (int)(o / hwp);
-  const int remp = (int)(o - (int64_t)n * hwp);
-  const int y = remp / Wp - a.pad, x = remp % Wp - a.pad;
+  const int rows_per = (Hp + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int y_lo = (int)blockIdx.y * rows_per, y_hi = min(Hp, y_lo + rows_per);
   const bool vec = a.dtype == ICF_BF16 && a.feat_pitch == 8;           // one 16-byte store per pixel
-  float f[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) f[j] = 0.f;
-  const bool inside = y >= 0 && y < a.H && x >= 0 && x < a.W;
-  if (!inside && !vec) {                                               // zero border
-    for (int ch = 0; ch < a.feat_pitch; ++ch) icf::st_any(a.feat, a.dtype, o * a.feat_pitch + ch, 0.f);
-    return;
+  const int n_emb = a.n_emb < ICF_MAX_PLANES - 1 ? a.n_emb : ICF_MAX_PLANES - 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int xp = threadIdx.x; xp < Wp; xp += EW_THREADS) {
+    const int x = xp - a.pad;
+    cxs[xp] = (uint8_t)((x >= 0 && x < a.W) ? min((x * 16) / a.W, 15) : 255);   // nearest: floor(dst*16/size); 255 = border
   }
-  if (inside) {
-    const int64_t i = ((int64_t)n * a.H + y) * a.W + x;                  // source pixel
-    const int cy = min((y * 16) / a.H, 15), cx = min((x * 16) / a.W, 15);   // nearest: floor(dst*16/size)
+  for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
     const float* mk = a.mask ? a.mask + (int64_t)n * a.mask_pitch : nullptr;
-    int ch = 0;
-    const float v = icf::ld_any(a.x, a.x_dtype, i * a.x_pitch);
-    f[0] = mk ? v * mk[0] : v;
-    ++ch;
+    for (int t = threadIdx.x; t < n_emb * 256; t += EW_THREADS) {
+      const int e = t >> 8, cell = t & 255;
+      const float v = tanhf(a.emb_table[e][(int64_t)a.emb_index[e][n] * 256 + cell]);
+      plane[e][cell] = (mk && 1 + e < 8) ? v * mk[1 + e] : v;
+    }
+    if ((int)threadIdx.x < a.n_cont && 1 + n_emb + (int)threadIdx.x < 8) {
+      const int ch = 1 + n_emb + (int)threadIdx.x;
+      const float v = a.cont[threadIdx.x][n];
+      cst[threadIdx.x] = mk ? v * mk[ch] : v;
+    }
+    if (threadIdx.x == 0) mk0 = mk ? mk[0] : 1.f;
+    __syncthreads();
+    // one warp per (padded) image row: no per-pixel division, the lanes walk the row
+    for (int yp = y_lo + warp; yp < y_hi; yp += EW_THREADS / 32) {
+      const int y = yp - a.pad;
+      const bool yin = y >= 0 && y < a.H;
+      const int crow = yin ? min((y * 16) / a.H, 15) * 16 : 0;
+      const int64_t orow = ((int64_t)n * Hp + yp) * Wp;
+      const int64_t irow = ((int64_t)n * a.H + (yin ? y : 0)) * a.W - a.pad;
+      for (int xp = lane; xp < Wp; xp += 32) {
+        const int cx = cxs[xp];
+        float f[8];
 #pragma unroll
-    for (int e = 0; e < ICF_MAX_PLANES - 1; ++e) {
-      if (e < a.n_emb) {
-        const float t = tanhf(a.emb_table[e][(int64_t)a.emb_index[e][n] * 256 + cy * 16 + cx]);
-        if (ch < 8) f[ch] = mk ? t * mk[ch] : t;
-        ++ch;
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+        if (yin && cx != 255) {
+          const int cell = crow + cx;
+          f[0] = icf::ld_any(a.x, a.x_dtype, (irow + xp) * a.x_pitch) * mk0;
+          int ch = 1;
+#pragma unroll
+          for (int e = 0; e < ICF_MAX_PLANES - 1; ++e)
+            if (e < n_emb) { f[ch] = plane[e][cell]; ++ch; }
+#pragma unroll
+          for (int e = 0; e < ICF_MAX_PLANES - 1; ++e)
+            if (e < a.n_cont && ch < 8) { f[ch] = cst[e]; ++ch; }
+        }
+        const int64_t o = orow + xp;
+        if (vec) {
+          uint4 w;
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
+          w.x = *reinterpret_cast<uint32_t*>(&p0); w.y = *reinterpret_cast<uint32_t*>(&p1);
+          w.z = *reinterpret_cast<uint32_t*>(&p2); w.w = *reinterpret_cast<uint32_t*>(&p3);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.feat) + o * 8) = w;
+        } else {
+          for (int ch = 0; ch < a.feat_pitch; ++ch) icf::st_any(a.feat, a.dtype, o * a.feat_pitch + ch, ch < 8 ? f[ch] : 0.f);
+        }
       }
     }
-#pragma unroll
-    for (int e = 0; e < ICF_MAX_PLANES - 1; ++e) {
-      if (e < a.n_cont) {
-        const float t = a.cont[e][n];
-        if (ch < 8) f[ch] = mk ? t * mk[ch] : t;
-        ++ch;
-      }
-    }
-  }
-  if (vec) {
-    uint4 w;
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
-    w.x = *reinterpret_cast<uint32_t*>(&p0); w.y = *reinterpret_cast<uint32_t*>(&p1);
-    w.z = *reinterpret_cast<uint32_t*>(&p2); w.w = *reinterpret_cast<uint32_t*>(&p3);
-    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.feat) + o * 8) = w;
-  } else {
-    for (int ch = 0; ch < a.feat_pitch; ++ch) icf::st_any(a.feat, a.dtype, o * a.feat_pitch + ch, ch < 8 ? f[ch] : 0.f);
+    __syncthreads();
   }
 }
 
@@ -447,6 +463,9 @@ __device__ __forceinline__ V8 ldf8(const float* p) {   // 8 consecutive floats, 
 }
 
 constexpr int VT = 256;          // threads per block of the vector kernels
+constexpr int GPB_MAX = 32;      // channel groups (of 8) a block spans: <= 32 keeps every reduction on the shuffle + row path of
+                                 // flush_partials (wider blocks fell into its shared-memory float-atomic path: the 512- and
+                                 // 1024-channel 1x1 layers paid 16-18 us for 4-8 MB tensors)
 constexpr int VSM = 2048;        // channels a block can hold partial sums for
 
 // flush per-thread channel partials, then one global atomic per channel per block.  Up to 256 channels per block
@@ -503,7 +522,7 @@ __device__ __forceinline__ void flush_partials(float (*acc)[8], int cbase_block,
 struct VMap { int c0, cbase_block, span; int64_t pix0, pstride, pix_end; };
 __device__ __forceinline__ VMap vmap(int C, int64_t pixels) {
   const int cg = C >> 3;
-  const int gpb = cg < VT ? cg : VT;                  // channel groups per block
+  const int gpb = cg < GPB_MAX ? cg : GPB_MAX;        // channel groups per block
   const int cblocks = (cg + gpb - 1) / gpb;           // blocks along channels
   const int cb = blockIdx.x % cblocks;
   const int64_t pb = blockIdx.x / cblocks, npb = gridDim.x / cblocks;
@@ -535,7 +554,7 @@ inline int vgrid(int C, int64_t pixels, int per_sm = 8) {
   static const int cap_env = env_int("ICF_EW_CAP");
   if (cap_env > 0) per_sm = cap_env;
   const int cg = C >> 3;
-  const int gpb = cg < VT ? cg : VT;
+  const int gpb = cg < GPB_MAX ? cg : GPB_MAX;
   const int cblocks = (cg + gpb - 1) / gpb;
   const int rows = VT / gpb;
   int64_t pblocks = (pixels + rows - 1) / rows;
@@ -843,11 +862,105 @@ __global__ void pack_kernel(const float* __restrict__ src, void* dst, int ddt, c
   }
 }
 
+// kind 0 body with 32-bit index arithmetic, for the jobs whose middle index (the filter tap) is contiguous in the source
+// (s1 == 1: every Conv2d / ConvTranspose2d weight).  A (row i0, 64-wide i2 chunk) tile goes through shared memory: it is READ
+// in source order (runs of d1 contiguous floats) and WRITTEN in packed order (128-byte runs of bf16), so both sides move whole
+// sectors.  Element-wise gathering of the packed order read one 4-byte element per 32-byte sector: 399 MB of L2->SM traffic
+// for 20 MB of weights (ncu, profiles/r02_ncu_small_kernels.txt), 70 us per network.
+constexpr int PK_CH = 64, PK_T = 32;
+__device__ __forceinline__ void pack_job_tiled(const icf_pack_job& jb, float* tile) {
+  const icf_perm& p = jb.p;
+  const uint32_t d0 = (uint32_t)p.d0, d1 = (uint32_t)p.d1, d2 = (uint32_t)p.d2, d2p = (uint32_t)p.d2_pad;
+  const uint32_t s0 = (uint32_t)p.s0, s2 = (uint32_t)p.s2;
+  const uint32_t chunks = (d2p + PK_CH - 1) / PK_CH, ntiles = (uint32_t)p.d0_pad * chunks;
+  for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const uint32_t i0 = t / chunks, c0 = (t - i0 * chunks) * PK_CH;
+    const uint32_t cw = min((uint32_t)PK_CH, d2p - c0);                  // chunk width (multiple of 8)
+    // load: e = i2l * d1 + i1 (source order)
+    for (uint32_t e = threadIdx.x; e < cw * d1; e += blockDim.x) {
+      const uint32_t i2l = e / d1, i1 = e - i2l * d1, i2 = c0 + i2l;
+      float v = 0.f;
+      if (i0 < d0 && i2 < d2) v = jb.src[i0 * s0 + i2 * s2 + i1];
+      tile[i1 * (PK_CH + 1) + i2l] = v;
+    }
+    __syncthreads();
+    // store: pairs of consecutive i2 (packed order)
+    const uint32_t hw = cw >> 1;
+    for (uint32_t e = threadIdx.x; e < hw * d1; e += blockDim.x) {
+      const uint32_t i1 = e / hw, pp = e - i1 * hw;
+      const float v0 = tile[i1 * (PK_CH + 1) + 2 * pp], v1 = tile[i1 * (PK_CH + 1) + 2 * pp + 1];
+      const uint32_t q = (((i0 * d1 + i1) * d2p) + c0) / 2 + pp;
+      if (jb.dst_dtype == ICF_F32) reinterpret_cast<float2*>(jb.dst)[q] = make_float2(v0, v1);
+      else reinterpret_cast<__nv_bfloat162*>(jb.dst)[q] = __floats2bfloat162_rn(v0, v1);
+    }
+    __syncthreads();
+  }
+}
+
+// 2-D transpose (d1 == 1, source contiguous along i0: the dgrad copy of a 1x1 conv / Linear weight): 32 x 64 tiles
+__device__ __forceinline__ void pack_job_transpose(const icf_pack_job& jb, float* tile) {
+  const icf_perm& p = jb.p;
+  const uint32_t d0 = (uint32_t)p.d0, d2 = (uint32_t)p.d2, d2p = (uint32_t)p.d2_pad, s2 = (uint32_t)p.s2, d0p = (uint32_t)p.d0_pad;
+  const uint32_t t0 = (d0p + 31) / 32, t2 = (d2p + PK_CH - 1) / PK_CH;
+  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 256 threads: 8 rows of 32
+  for (uint32_t t = blockIdx.x; t < t0 * t2; t += gridDim.x) {
+    const uint32_t b0 = (t / t2) * 32, b2 = (t % t2) * PK_CH;
+    for (uint32_t r = ty; r < PK_CH; r += 8) {                           // tile[i2l][i0l], coalesced along i0
+      const uint32_t i0 = b0 + tx, i2 = b2 + r;
+      tile[r * 33 + tx] = (i0 < d0 && i2 < d2) ? jb.src[i0 + i2 * s2] : 0.f;
+    }
+    __syncthreads();
+    for (uint32_t r = ty; r < 32; r += 8) {                              // one packed row (i0) per warp pass, 32 pairs along i2
+      const uint32_t i0 = b0 + r, i2 = b2 + 2 * tx;
+      if (i0 < d0p && i2 < d2p) {
+        const float v0 = tile[(2 * tx) * 33 + r], v1 = tile[(2 * tx + 1) * 33 + r];
+        const uint32_t q = (i0 * d2p + i2) >> 1;
+        if (jb.dst_dtype == ICF_F32) reinterpret_cast<float2*>(jb.dst)[q] = make_float2(v0, v1);
+        else reinterpret_cast<__nv_bfloat162*>(jb.dst)[q] = __floats2bfloat162_rn(v0, v1);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// same arithmetic without the tile (any strides): two packed elements per thread
+__device__ __forceinline__ void pack_job32(const icf_pack_job& jb) {
+  const icf_perm& p = jb.p;
+  const uint32_t d2p = (uint32_t)p.d2_pad, d1 = (uint32_t)p.d1, d2 = (uint32_t)p.d2, d0 = (uint32_t)p.d0;
+  const uint32_t s0 = (uint32_t)p.s0, s1 = (uint32_t)p.s1, s2 = (uint32_t)p.s2;
+  const uint32_t pairs = (uint32_t)((p.d0_pad * p.d1 * p.d2_pad) >> 1);          // d2_pad is even on this path
+  const uint32_t half = d2p >> 1;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < pairs; q += gridDim.x * blockDim.x) {
+    const uint32_t t = q / half, i2 = (q - t * half) * 2;
+    const uint32_t i0 = t / d1, i1 = t - i0 * d1;
+    float v0 = 0.f, v1 = 0.f;
+    if (i0 < d0) {
+      const uint32_t base = i0 * s0 + i1 * s1 + i2 * s2;
+      if (i2 < d2) v0 = jb.src[base];
+      if (i2 + 1 < d2) v1 = jb.src[base + s2];
+    }
+    if (jb.dst_dtype == ICF_F32) {
+      reinterpret_cast<float2*>(jb.dst)[q] = make_float2(v0, v1);
+    } else {
+      reinterpret_cast<__nv_bfloat162*>(jb.dst)[q] = __floats2bfloat162_rn(v0, v1);
+    }
+  }
+}
+
 __global__ void pack_multi_kernel(const icf_pack_job* __restrict__ jobs) {
+  __shared__ float pk_tile[PK_CH * 33 + 64];   // >= PK_T * (PK_CH + 1) (tap tiles) and PK_CH * 33 (transpose tiles)
   const icf_pack_job jb = jobs[blockIdx.y];
   if (jb.kind == 0) {
     const icf_perm p = jb.p;
     const int64_t total = p.d0_pad * p.d1 * p.d2_pad;
+    const int64_t src_span = (p.d0 - 1) * p.s0 + (p.d1 - 1) * p.s1 + (p.d2 - 1) * p.s2;
+    if ((p.d2_pad & 1) == 0 && total < 0x7fffffffLL && src_span < 0x7fffffffLL && p.d0 > 0 && p.d1 > 0 && p.d2 > 0 &&
+        (reinterpret_cast<uintptr_t>(jb.dst) & 7) == 0) {
+      if (p.s1 == 1 && p.d1 <= PK_T && (p.d2_pad & 7) == 0 && p.d1 > 1) pack_job_tiled(jb, pk_tile);
+      else if (p.d1 == 1 && p.s0 == 1 && p.s2 > 1 && blockDim.x == 256) pack_job_transpose(jb, pk_tile);
+      else pack_job32(jb);
+      return;
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
       const int64_t i2 = i % p.d2_pad;
       const int64_t t = i / p.d2_pad;
@@ -981,7 +1094,12 @@ int icf_image_features_fwd(const icf_imgfeat_args* a, void* stream) {
               a->n_cont, a->feat_pitch);
   const int64_t total = (int64_t)a->N * (a->H + 2 * a->pad) * (a->W + 2 * a->pad);
   if (total == 0) return 0;
-  imgfeat_fwd_kernel<<<icf::cdiv(total, EW_THREADS), EW_THREADS, 0, icf::as_stream(stream)>>>(*a);
+  const int sms = icf::sm_count();
+  const int Hp = a->H + 2 * a->pad, Wp = a->W + 2 * a->pad;
+  ICF_REQUIRE(Wp <= 640 && Hp <= 65535, "icf_image_features_fwd: images wider than 640 (padded) are not supported");
+  int gx = a->N < sms * 8 ? a->N : sms * 8, gy = 1;
+  while (gx * gy < 2 * sms && Hp / (gy * 2) >= 8 && gy < 64) gy *= 2;            // few, large images: split the rows
+  imgfeat_fwd_kernel<<<dim3((unsigned)gx, (unsigned)gy), EW_THREADS, 0, icf::as_stream(stream)>>>(*a);
   return icf::check_launch("imgfeat_fwd");
 }
 

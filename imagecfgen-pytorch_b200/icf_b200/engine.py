@@ -326,6 +326,7 @@ class NetExec:
         self._wg_key = None
         self._scratch = None
         self.bn_sync = None                         # icf_b200.dp.Group: BatchNorm statistics span all ranks (SyncBN)
+        self.idx_cache = None                       # per-step cache of attribute argmax indices (set by the trainers)
         self.keep_state = False                     # tests: keep the saved activations of the last forward
         self.last_state = None
         self.emb_key = 2 if role != "G" else 3      # index into fam.cat_attrs tuples
@@ -555,10 +556,21 @@ class NetExec:
             return names
         return list(self.fam.cont_attrs)
 
+    def _argmax(self, t):
+        """argmax(1) of a one-hot attribute; inside one train step the same attribute tensors feed two E and six D forwards,
+        so the trainer lends a per-step cache (never kept across steps: a replayed CUDA graph must recompute it)."""
+        cache = self.idx_cache
+        if cache is None:
+            return ops.argmax_rows(t.detach())
+        key = (t.data_ptr(), tuple(t.shape), t.dtype)
+        if key not in cache:
+            cache[key] = ops.argmax_rows(t.detach())
+        return cache[key]
+
     def _image_feats(self, N, x_ptr, x_code, x_pitch, c, mask):
         ts = self.tensors()
         cats, conts = self._attr_inputs(c, N)
-        idx = [ops.argmax_rows(t.detach()) for t in cats]
+        idx = [self._argmax(t) for t in cats]
         tables = [ts[a[self.emb_key]] for a in self.fam.cat_attrs]
         first = self.towers["E" if self.role == "E" else "Dx"].layers[0]
         fpad = first.pad if first.fold else 0            # folded first conv reads a zero-bordered tensor

@@ -175,6 +175,7 @@ class BiGANTrainer:
         dl = torch.empty((N, 1), dtype=torch.float32, device=self.device)
         dl2 = torch.empty((N, 1), dtype=torch.float32, device=self.device)
 
+        exE.idx_cache = exD.idx_cache = {}            # attribute argmax indices: computed once per step
         with torch.cuda.device(self.device):
             # ---- Phase A: encoder + generator update (mnist.py:224-230) --------------------------------
             if phase_a:
@@ -230,6 +231,7 @@ class BiGANTrainer:
             ops.sigmoid_mean(l.ptr, F32, 1, N, ops.ptr(out, 3))
             l, _ = exD.discriminator_forward(N, xp, xc, 1, zE.ptr, zE.code, zE.pitch, c, masks=masks6[5], save=False)
             ops.sigmoid_mean(l.ptr, F32, 1, N, ops.ptr(out, 4))
+        exE.idx_cache = exD.idx_cache = None
         return out
 
     # ---- CUDA graph -------------------------------------------------------------------------------------

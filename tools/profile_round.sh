@@ -6,7 +6,7 @@
 # usage: tools/profile_round.sh <tag>
 set -u
 TAG=${1:-r01}
-CMD="python bench.py --steps 2 --warmup 3 --skip-cf --skip-cpu --no-graph"
+CMD="python bench.py --steps 2 --warmup 3 --skip-cf --skip-cpu --skip-torch --no-graph"
 timeout 300 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
 if [ -z "${SKIP_LIST:-}" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 1400 --csv \
