@@ -21,6 +21,7 @@ using namespace icf_tc;
 constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
 constexpr int MAX_CLASSES = 16, MAX_TAPS = 25;
 constexpr int NUM_THREADS = 192;
+inline int tc_sm_count() { return icf::sm_count(); }
 
 struct TapTable {
   int16_t ntaps[MAX_CLASSES];
@@ -48,51 +49,65 @@ struct TcParams {
 };
 
 // ------------------------------------------------------------------------------------------------
-// forward / dgrad kernel
+// forward / dgrad kernel — PERSISTENT: a CTA walks tiles t = blockIdx.x, += gridDim.x (the grid is one resident wave).
+// The shared-memory ring and its phases run on across tiles; with ACC = 2 the TMEM accumulator is double-buffered so
+// that the epilogue of tile t (TMEM -> bias / activation / Dropout2d mask -> global) overlaps the TMA + MMA main loop of
+// tile t+1 — most layers of these networks have short K loops (1-4 taps of a stride-2 class x 2-4 channel chunks), where
+// the one-tile-per-CTA version spent more time in barrier set-up, TMEM allocation, pipeline fill and the epilogue than in
+// the MMAs.  ACC = 1 (256-wide tiles: 2 x 256 columns would take the whole TMEM and forbid a second CTA per SM) keeps a
+// single accumulator; there the second resident CTA provides the overlap.
 // ------------------------------------------------------------------------------------------------
-template <int TILE_N, int STAGES>
+struct TileCoord {
+  int cls, py, px, Pi, Qj, i0, j0, n0, k0;
+  bool inside;
+};
+
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t, int tile_n) {
+  TileCoord c;
+  const int kt = t % p.tiles_k; t /= p.tiles_k;
+  const int jt = t % p.tiles_j; t /= p.tiles_j;
+  const int it = t % p.tiles_i; t /= p.tiles_i;
+  const int nt = t % p.tiles_n;
+  c.cls = t / p.tiles_n;
+  c.py = c.cls / p.ostep;
+  c.px = c.cls - c.py * p.ostep;
+  c.Pi = (p.P - c.py + p.ostep - 1) / p.ostep;
+  c.Qj = (p.Q - c.px + p.ostep - 1) / p.ostep;
+  c.i0 = it * p.ti; c.j0 = jt * p.tj; c.n0 = nt * p.tn; c.k0 = kt * tile_n;
+  c.inside = c.i0 < c.Pi && c.j0 < c.Qj;     // false: the tile lies outside this (smaller) parity class
+  return c;
+}
+
+// a tap is live for a tile when its source box touches the un-padded input
+__device__ __forceinline__ bool tap_live(const TcParams& p, const TileCoord& c, int ti_) {
+  const int ylo = c.i0 * p.sstep + p.tt.dy[c.cls][ti_], yhi = ylo + (p.ti - 1) * p.sstep;
+  const int xlo = c.j0 * p.sstep + p.tt.dx[c.cls][ti_], xhi = xlo + (p.tj - 1) * p.sstep;
+  return yhi >= 0 && ylo < p.H && xhi >= 0 && xlo < p.W;
+}
+
+template <int TILE_N, int STAGES, int ACC>
 __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                               const __grid_constant__ CUtensorMap map_b,
                                                               const __grid_constant__ TcParams p) {
   constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   constexpr uint32_t B_BYTES = TILE_N * BLOCK_K * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int TMEM_COLS = TILE_N < 32 ? 32 : TILE_N;
+  constexpr int ACC_COLS = TILE_N < 32 ? 32 : TILE_N;
+  constexpr int TMEM_COLS = ACC * ACC_COLS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);   // full[S], empty[S], tmem_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);   // full[S] empty[S] tmem_full[2] tmem_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* sbias = reinterpret_cast<float*>(bars + 16);           // TILE_N floats, 128 B past the barriers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // ---- tile coordinates ---------------------------------------------------------------------------
-  int t = blockIdx.x;
-  const int kt = t % p.tiles_k; t /= p.tiles_k;
-  const int jt = t % p.tiles_j; t /= p.tiles_j;
-  const int it = t % p.tiles_i; t /= p.tiles_i;
-  const int nt = t % p.tiles_n;
-  const int cls = t / p.tiles_n;
-  const int py = cls / p.ostep, px = cls - py * p.ostep;
-  const int Pi = (p.P - py + p.ostep - 1) / p.ostep, Qj = (p.Q - px + p.ostep - 1) / p.ostep;
-  const int i0 = it * p.ti, j0 = jt * p.tj, n0 = nt * p.tn, k0 = kt * TILE_N;
-  if (i0 >= Pi || j0 >= Qj) return;   // tile lies outside this (smaller) parity class
-
-  // taps of this class whose source box touches the un-padded input
-  const int ntaps = p.tt.ntaps[cls];
-  auto tap_live = [&](int ti_) -> bool {
-    const int ylo = i0 * p.sstep + p.tt.dy[cls][ti_], yhi = ylo + (p.ti - 1) * p.sstep;
-    const int xlo = j0 * p.sstep + p.tt.dx[cls][ti_], xhi = xlo + (p.tj - 1) * p.sstep;
-    return yhi >= 0 && ylo < p.H && xhi >= 0 && xlo < p.W;
-  };
-  int live = 0;
-  for (int i = 0; i < ntaps; ++i) live += tap_live(i) ? 1 : 0;
-  const int n_iters = live * p.kchunks;
+  const int total_tiles = p.n_classes * p.tiles_n * p.tiles_i * p.tiles_j * p.tiles_k;
 
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  auto tmem_full_bar = [&](int b_) { return bar_base + 8u * (2 * STAGES + b_); };
+  auto tmem_empty_bar = [&](int b_) { return bar_base + 8u * (2 * STAGES + 2 + b_); };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a);
@@ -101,7 +116,10 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b_ = 0; b_ < 2; ++b_) {
+      mbar_init(tmem_full_bar(b_), 1);
+      mbar_init(tmem_empty_bar(b_), 4);      // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
@@ -111,33 +129,48 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer (warp-uniform loop, the elected lane issues) =====
-    {
-      const uint32_t leader = elect_one();
-      int iter = 0;
+    // ===== TMA producer (warp-uniform loops, the elected lane issues) =====
+    const uint32_t leader = elect_one();
+    int iter = 0;                                  // ring position, runs on across tiles
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord c = tile_coord(p, t, TILE_N);
+      if (!c.inside) continue;
+      const int ntaps = p.tt.ntaps[c.cls];
       for (int ti_ = 0; ti_ < ntaps; ++ti_) {
-        if (!tap_live(ti_)) continue;
-        const int y = i0 * p.sstep + p.tt.dy[cls][ti_], x = j0 * p.sstep + p.tt.dx[cls][ti_];
-        const int wcol = p.tt.tap[cls][ti_] * p.w_pitch;
+        if (!tap_live(p, c, ti_)) continue;
+        const int y = c.i0 * p.sstep + p.tt.dy[c.cls][ti_], x = c.j0 * p.sstep + p.tt.dx[c.cls][ti_];
+        const int wcol = p.tt.tap[c.cls][ti_] * p.w_pitch;
         for (int kc = 0; kc < p.kchunks; ++kc, ++iter) {
           const int s = iter % STAGES;
           mbar_wait(empty_bar(s), ((iter / STAGES) & 1) ^ 1);
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
           mbar_expect_tx_if(full_bar(s), p.a_tx_bytes + B_BYTES, leader);
-          tma_load_4d_if(sa, &map_a, full_bar(s), kc * BLOCK_K, x, y, n0, leader);
-          tma_load_2d_if(sb, &map_b, full_bar(s), wcol + kc * BLOCK_K, k0, leader);
+          tma_load_4d_if(sa, &map_a, full_bar(s), kc * BLOCK_K, x, y, c.n0, leader);
+          tma_load_2d_if(sb, &map_b, full_bar(s), wcol + kc * BLOCK_K, c.k0, leader);
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp runs the loop, one elected lane issues (inside an `if (lane == 0)` region
     // every tcgen05.mma cost ~190 cycles of warp time, in warp-uniform code ~90: measured on the scatter kernel) =====
-    {
-      const uint32_t leader = elect_one();
-      constexpr uint32_t idesc = make_idesc(BLOCK_M, TILE_N, 0, 0);
-      const uint64_t d0 = make_desc(0, 16, 1024);
-      const uint32_t desc_hi = (uint32_t)(d0 >> 32), desc_lo = (uint32_t)d0;      // low word without an address
-      for (int iter = 0; iter < n_iters; ++iter) {
+    const uint32_t leader = elect_one();
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, TILE_N, 0, 0);
+    const uint64_t d0 = make_desc(0, 16, 1024);
+    const uint32_t desc_hi = (uint32_t)(d0 >> 32), desc_lo = (uint32_t)d0;      // low word without an address
+    int iter = 0, done = 0;                        // ring position; tiles this CTA has accumulated so far
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord c = tile_coord(p, t, TILE_N);
+      if (!c.inside) continue;
+      const int ntaps = p.tt.ntaps[c.cls];
+      int live = 0;
+      for (int i = 0; i < ntaps; ++i) live += tap_live(p, c, i) ? 1 : 0;
+      const int n_iters = live * p.kchunks;
+      const int b_ = ACC == 2 ? (done & 1) : 0;
+      const int use = ACC == 2 ? (done >> 1) : done;
+      mbar_wait(tmem_empty_bar(b_), (use & 1) ^ 1);          // the epilogue has drained this accumulator (first use: free)
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(b_ * ACC_COLS);
+      for (int i = 0; i < n_iters; ++i, ++iter) {
         const int s = iter % STAGES;
         mbar_wait(full_bar(s), (iter / STAGES) & 1);
         tc_fence_after();
@@ -145,78 +178,102 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
         const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | desc_lo, b_lo = ((sb >> 4) & 0x3FFFu) | desc_lo;
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-          umma_bf16_lo(tmem_base, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (iter | k) ? 1u : 0u, leader);
+          umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (i | k) ? 1u : 0u, leader);
         umma_commit_if(empty_bar(s), leader);
       }
-      if (n_iters > 0) umma_commit_if(tmem_full_bar, leader);
-      else if (lane == 0) mbar_arrive(tmem_full_bar);
+      if (n_iters > 0) umma_commit_if(tmem_full_bar(b_), leader);
+      else if (lane == 0) mbar_arrive(tmem_full_bar(b_));
+      ++done;
     }
   } else {
     // ===== epilogue: one D row (TMEM lane) per thread =====
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;
-    // bias tile -> shared memory (zero where absent / beyond K), visible to the four epilogue warps
-    for (int j = (int)threadIdx.x - 64; j < TILE_N; j += 128) sbias[j] = (p.bias && k0 + j < p.K) ? __ldg(p.bias + k0 + j) : 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
     const int tij = p.ti * p.tj;
     const int tn_i = m / tij, rem = m - tn_i * tij;
     const int ti_i = rem / p.tj, tj_i = rem - ti_i * p.tj;
-    const int n = n0 + tn_i, ii = i0 + ti_i, jj = j0 + tj_i;
-    const bool valid = (tn_i < p.tn) && n < p.N && ii < Pi && jj < Qj;
-    const int op = py + ii * p.ostep, oq = px + jj * p.ostep;
-    const int64_t pix = valid ? ((int64_t)n * p.P + op) * p.Q + oq : 0;
-    const float* mrow = (p.mask && valid) ? p.mask + (int64_t)n * p.mask_pitch + k0 : nullptr;
     const int esize = p.out_f32 ? 4 : 2;
-    uint8_t* orow = reinterpret_cast<uint8_t*>(p.dst) + (pix * p.out_pitch + k0) * esize;
-    // Dropout2d mask of this thread's row: while the main loop runs (these warps would idle on tmem_full) its lines are
-    // pulled into L2, and the 16 values of group g+1 are loaded (four 16-byte loads) while group g is in the math — a
-    // 1x1-spatial layer reads one mask row PER OUTPUT ROW; fetched on demand, 16 scalar loads per group from DRAM held the
-    // 64-CTA GEMMs at ~35 us (ncu: the epilogue's FMUL waits on them, profiles/r01_final_stall_summary.txt).
-    const int kcols = (p.K - k0) < TILE_N ? (p.K - k0) : TILE_N;
-    const bool mvec = mrow && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0) && (kcols & 15) == 0;
-    if (mrow) {
-      for (int j = 0; j < kcols; j += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(mrow + j));
-    }
-    float mk[16], mk_next[16];
+    int done = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord c = tile_coord(p, t, TILE_N);
+      if (!c.inside) continue;
+      const int k0 = c.k0;
+      const int ntaps = p.tt.ntaps[c.cls];
+      int live = 0;
+      for (int i = 0; i < ntaps; ++i) live += tap_live(p, c, i) ? 1 : 0;
+      const int n_iters = live * p.kchunks;
+      // bias tile -> shared memory (zero where absent / beyond K), visible to the four epilogue warps; the first barrier
+      // keeps a fast warp from overwriting the previous tile's bias while a slow one still reads it
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int j = (int)threadIdx.x - 64; j < TILE_N; j += 128) sbias[j] = (p.bias && k0 + j < p.K) ? __ldg(p.bias + k0 + j) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int n = c.n0 + tn_i, ii = c.i0 + ti_i, jj = c.j0 + tj_i;
+      const bool valid = (tn_i < p.tn) && n < p.N && ii < c.Pi && jj < c.Qj;
+      const int op = c.py + ii * p.ostep, oq = c.px + jj * p.ostep;
+      const int64_t pix = valid ? ((int64_t)n * p.P + op) * p.Q + oq : 0;
+      const float* mrow = (p.mask && valid) ? p.mask + (int64_t)n * p.mask_pitch + k0 : nullptr;
+      uint8_t* orow = reinterpret_cast<uint8_t*>(p.dst) + (pix * p.out_pitch + k0) * esize;
+      // Dropout2d mask of this thread's row: while the main loop runs (these warps would idle on tmem_full) its lines are
+      // pulled into L2, and the 16 values of group g+1 are loaded (four 16-byte loads) while group g is in the math — a
+      // 1x1-spatial layer reads one mask row PER OUTPUT ROW; fetched on demand, 16 scalar loads per group from DRAM held the
+      // 64-CTA GEMMs at ~35 us (ncu: the epilogue's FMUL waits on them, profiles/r01_final_stall_summary.txt).
+      const int kcols = (p.K - k0) < TILE_N ? (p.K - k0) : TILE_N;
+      const bool mvec = mrow && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0) && (kcols & 15) == 0;
+      if (mrow) {
+        for (int j = 0; j < kcols; j += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(mrow + j));
+      }
+      float mk[16], mk_next[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) mk_next[j] = 1.f;
-    auto load_mask = [&](int c0) {
-      if (!mrow) return;
-      if (mvec) {
+      for (int j = 0; j < 16; ++j) mk_next[j] = 1.f;
+      auto load_mask = [&](int c0) {
+        if (!mrow) return;
+        if (mvec) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(mrow + c0 + j));
-          mk_next[j] = t.x; mk_next[j + 1] = t.y; mk_next[j + 2] = t.z; mk_next[j + 3] = t.w;
+          for (int j = 0; j < 16; j += 4) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(mrow + c0 + j));
+            mk_next[j] = t4.x; mk_next[j + 1] = t4.y; mk_next[j + 2] = t4.z; mk_next[j + 3] = t4.w;
+          }
+        } else {
+          const int nv = p.K - (k0 + c0);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mk_next[j] = (j < nv) ? __ldg(mrow + c0 + j) : 0.f;
         }
-      } else {
-        const int nv = p.K - (k0 + c0);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) mk_next[j] = (j < nv) ? __ldg(mrow + c0 + j) : 0.f;
-      }
-    };
-    load_mask(0);
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+      };
+      load_mask(0);
+      const int b_ = ACC == 2 ? (done & 1) : 0;
+      const int use = ACC == 2 ? (done >> 1) : done;
+      mbar_wait(tmem_full_bar(b_), use & 1);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b_ * ACC_COLS);
+      const int ngroups = (kcols + 15) >> 4;
 #pragma unroll 1
-    for (int c0 = 0; c0 < TILE_N; c0 += 16) {
-      const int nv = p.K - (k0 + c0);
-      if (nv <= 0) break;            // uniform across the CTA
-      uint32_t v[16];
-      if (n_iters > 0) {
-        tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, v);
-      } else {
+      for (int g = 0; g < ngroups; ++g) {
+        const int c0 = g * 16;
+        const int nv = p.K - (k0 + c0);
+        uint32_t v[16];
+        if (n_iters > 0) {
+          tmem_ld16(t_acc + (uint32_t)c0, v);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0u;
+          for (int j = 0; j < 16; ++j) v[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) mk[j] = mk_next[j];
+        if (g + 1 < ngroups) load_mask(c0 + 16);                  // next group's mask, in flight during this group's math
+        if (n_iters > 0) tmem_ld_wait();
+        if (g + 1 == ngroups) {
+          // the accumulator has been read completely: hand it back before the math and the stores of the last group
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(b_));
+        }
+        if (!valid) continue;
+        const int nvl = nv < 16 ? nv : 16;
+        int npad = (nvl + 7) & ~7;
+        if (k0 + c0 + npad > p.out_pitch) npad = nvl;
+        epi16(v, sbias + c0, mk, p.act, p.slope, nvl, npad, p.out_f32, orow + c0 * esize);
       }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) mk[j] = mk_next[j];
-      if (nv > 16 && c0 + 16 < TILE_N) load_mask(c0 + 16);      // next group's mask, in flight during this group's math
-      if (n_iters > 0) tmem_ld_wait();
-      if (!valid) continue;
-      const int nvl = nv < 16 ? nv : 16;
-      int npad = (nvl + 7) & ~7;
-      if (k0 + c0 + npad > p.out_pitch) npad = nvl;
-      epi16(v, sbias + c0, mk, p.act, p.slope, nvl, npad, p.out_f32, orow + c0 * esize);
+      ++done;
     }
   }
   tc_fence_before();
@@ -386,15 +443,15 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
   if (warp == 1) tmem_dealloc_rt(tmem_base, p.tmem_cols);
 }
 
-int tc_sm_count() { return icf::sm_count(); }
-
-template <int TILE_N, int STAGES>
-int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int64_t grid, cudaStream_t st) {
+template <int TILE_N, int STAGES, int ACC>
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int64_t tiles, int ctas_per_sm, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + TILE_N * BLOCK_K * 2) + 1024 + 256 + 1024;
   // the attribute is per device and idempotent: set it on every device this thread launches on, race-free across threads
   static icf::SmemGuard guard;
-  if (int r = guard.ensure(reinterpret_cast<const void*>(conv_tc_kernel<TILE_N, STAGES>), smem, "tensor-core conv")) return r;
-  conv_tc_kernel<TILE_N, STAGES><<<(unsigned)grid, NUM_THREADS, smem, st>>>(ma, mb, p);
+  if (int r = guard.ensure(reinterpret_cast<const void*>(conv_tc_kernel<TILE_N, STAGES, ACC>), smem, "tensor-core conv")) return r;
+  int64_t grid = (int64_t)tc_sm_count() * ctas_per_sm;       // one resident wave of persistent CTAs
+  if (grid > tiles) grid = tiles;
+  conv_tc_kernel<TILE_N, STAGES, ACC><<<(unsigned)grid, NUM_THREADS, smem, st>>>(ma, mb, p);
   return icf::check_launch("conv_tc");
 }
 
@@ -497,17 +554,18 @@ int icf_tc_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   int r;
   switch (tile_n) {
     case 256: {
-      // 2 stages = 96 KB: two CTAs per SM, one CTA's epilogue overlaps the other's main loop.  Measured: 8-18 % faster when
-      // the grid is at least ~1.5 waves (G.layers.2 fprop, the 256-wide dgrads, the 771->4608 GEMM), 20-40 % slower on the
-      // 64-128 CTA grids of the 1x1-spatial layers, which keep the 4-stage ring (ICF_TC_256_STAGES=2|4 forces either)
+      // 2 stages = 96 KB and one 256-column accumulator: two CTAs per SM, one CTA's epilogue overlaps the other's main loop.
+      // Measured (round 1, one tile per CTA): 8-18 % faster when the grid is at least ~1.5 waves (G.layers.2 fprop, the 256-wide
+      // dgrads, the 771->4608 GEMM), 20-40 % slower on small grids, which keep the 4-stage ring with one CTA per SM
+      // (ICF_TC_256_STAGES=2|4 forces either)
       static const int st_env = []() { const char* e = getenv("ICF_TC_256_STAGES"); return e ? atoi(e) : 0; }();
       const bool two = st_env == 2 || (st_env != 4 && grid >= 220);
-      r = two ? launch_tc<256, 2>(ma, mb, p, grid, st) : launch_tc<256, 4>(ma, mb, p, grid, st);
+      r = two ? launch_tc<256, 2, 1>(ma, mb, p, grid, 2, st) : launch_tc<256, 4, 2>(ma, mb, p, grid, 1, st);
       break;
     }
-    case 128: r = launch_tc<128, 3>(ma, mb, p, grid, st); break;
-    case 64: r = launch_tc<64, 4>(ma, mb, p, grid, st); break;
-    default: r = launch_tc<32, 4>(ma, mb, p, grid, st); break;
+    case 128: r = launch_tc<128, 3, 2>(ma, mb, p, grid, 2, st); break;
+    case 64: r = launch_tc<64, 4, 2>(ma, mb, p, grid, 2, st); break;
+    default: r = launch_tc<32, 4, 2>(ma, mb, p, grid, 2, st); break;
   }
   if (r) return r;
   if (a->stats) {
