@@ -215,22 +215,29 @@ __global__ void __launch_bounds__(NT) wgrad_simt_kernel(const icf_wgrad_args a, 
 // images, keeps the image's dY plane in shared memory (broadcast reads), lane = channel pair, warp = pixel.
 // ------------------------------------------------------------------------------------------------
 template <int KS>
-__global__ void __launch_bounds__(256) wgrad_b1_kernel(const icf_wgrad_args a) {
-  extern __shared__ float sdy[];                   // [H*W] of the current image, then [8][KS*KS][64] reduction scratch
+__global__ void __launch_bounds__(256) wgrad_b1_kernel(const icf_wgrad_args a, int band_rows, int bands, int dy_rows_max) {
+  extern __shared__ float sdy[];                   // [dy_rows_max * W] rows of the current band, then [8][KS*KS][64] scratch
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int HW = a.H * a.W, PQ = a.P * a.Q;
   const __nv_bfloat16* __restrict__ sm = reinterpret_cast<const __nv_bfloat16*>(a.small_t);
   const __nv_bfloat16* __restrict__ bg = reinterpret_cast<const __nv_bfloat16*>(a.big_t);
+  const int items = a.N * bands;
   for (int a0 = 0; a0 < a.A; a0 += 64) {           // 64 channels per pass (one bf16 pair per lane)
     float acc[KS * KS][2];
 #pragma unroll
     for (int t = 0; t < KS * KS; ++t) acc[t][0] = acc[t][1] = 0.f;
     const int ch = a0 + 2 * lane;
-    for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
+    // work item = (image, band of rows of X): only the dY rows that band touches are staged (a 512 x 512 plane does not fit
+    // shared memory; whole-image items also left a batch of 64 on 64 of the 148 SMs)
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int n = item / bands, band = item - n * bands;
+      const int p_lo = band * band_rows, p_hi = min(a.P, p_lo + band_rows);
+      const int y_lo = max(0, p_lo * a.stride - a.pad), y_hi = min(a.H, (p_hi - 1) * a.stride - a.pad + KS);
       __syncthreads();
-      for (int i = threadIdx.x; i < HW; i += blockDim.x) sdy[i] = __bfloat162float(bg[((int64_t)n * HW + i) * a.b_pitch]);
+      for (int i = threadIdx.x; i < (y_hi - y_lo) * a.W; i += blockDim.x)
+        sdy[i] = __bfloat162float(bg[((int64_t)n * HW + (int64_t)y_lo * a.W + i) * a.b_pitch]);
       __syncthreads();
-      for (int pix = warp; pix < PQ; pix += 8) {
+      for (int pix = p_lo * a.Q + warp; pix < p_hi * a.Q; pix += 8) {
         const int p = pix / a.Q, q = pix - p * a.Q;
         float x0 = 0.f, x1 = 0.f;
         if (ch + 1 < a.A) {
@@ -244,11 +251,11 @@ __global__ void __launch_bounds__(256) wgrad_b1_kernel(const icf_wgrad_args a) {
 #pragma unroll
         for (int r = 0; r < KS; ++r) {
           const int y = y0 + r;
-          const bool yin = y >= 0 && y < a.H;
+          const bool yin = y >= y_lo && y < y_hi;
 #pragma unroll
           for (int c = 0; c < KS; ++c) {
             const int x = xx0 + c;
-            const float v = (yin && x >= 0 && x < a.W) ? sdy[y * a.W + x] : 0.f;
+            const float v = (yin && x >= 0 && x < a.W) ? sdy[(y - y_lo) * a.W + x] : 0.f;
             acc[r * KS + c][0] = fmaf(x0, v, acc[r * KS + c][0]);
             acc[r * KS + c][1] = fmaf(x1, v, acc[r * KS + c][1]);
           }
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__(256) wgrad_b1_kernel(const icf_wgrad_args a) {
     }
     // cross-warp reduction, then one atomic per (channel, tap) and block
     __syncthreads();
-    float* red = sdy + HW;
+    float* red = sdy + (size_t)dy_rows_max * a.W;
 #pragma unroll
     for (int t = 0; t < KS * KS; ++t) {
       red[(warp * KS * KS + t) * 64 + 2 * lane] = acc[t][0];
@@ -277,12 +284,24 @@ __global__ void __launch_bounds__(256) wgrad_b1_kernel(const icf_wgrad_args a) {
 
 template <int KS>
 int launch_wgrad_b1(const icf_wgrad_args* a, cudaStream_t st) {
-  const size_t smem = ((size_t)a->H * a->W + 8 * KS * KS * 64) * sizeof(float);
+  // rows of X per work item: as many as keep the staged dY rows within ~48 KB, and enough items to fill the machine twice
+  const int sms = icf::sm_count();
+  int band_rows = a->P;
+  auto dy_rows = [&](int br) { return (br - 1) * a->stride + KS; };
+  while (band_rows > 1 && ((size_t)dy_rows(band_rows) * a->W * sizeof(float) > 48 * 1024 ||
+                           (int64_t)a->N * icf::cdiv(a->P, band_rows) < 2 * sms))
+    band_rows = (band_rows + 1) / 2;
+  const int bands = icf::cdiv(a->P, band_rows);
+  int dy_rows_max = dy_rows(band_rows);
+  if (dy_rows_max > a->H) dy_rows_max = a->H;
+  const size_t smem = ((size_t)dy_rows_max * a->W + 8 * KS * KS * 64) * sizeof(float);
+  if (smem > 200 * 1024) return -1;
   static icf::SmemGuard guard;
   if (smem > 48 * 1024 && guard.ensure(reinterpret_cast<const void*>(wgrad_b1_kernel<KS>), smem, "single-channel wgrad")) return -1;
-  const int cap = icf::sm_count() * 4;
-  int grid = a->N < cap ? a->N : cap;
-  wgrad_b1_kernel<KS><<<grid, 256, smem, st>>>(*a);
+  const int64_t items = (int64_t)a->N * bands;
+  const int cap = sms * 2;
+  const int grid = (int)(items < cap ? items : cap);
+  wgrad_b1_kernel<KS><<<grid, 256, smem, st>>>(*a, band_rows, bands, dy_rows_max);
   return icf::check_launch("wgrad_b1");
 }
 
@@ -329,7 +348,6 @@ int icf_simt_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
 int icf_b1_conv_wgrad(const icf_wgrad_args* a, cudaStream_t st) {
   if (a->dtype != ICF_BF16 || a->B != 1 || a->win > 1 || a->R != a->S || (a->a_pitch & 1)) return -1;
   if ((reinterpret_cast<uintptr_t>(a->small_t) & 3) != 0) return -1;
-  if (((size_t)a->H * a->W + 8 * 25 * 64) * sizeof(float) > 200 * 1024) return -1;
   switch (a->R) {
     case 3: return launch_wgrad_b1<3>(a, st);
     case 4: return launch_wgrad_b1<4>(a, st);

@@ -127,6 +127,39 @@ __global__ void __launch_bounds__(LT) onehot_swap_kernel(const void* idx, int id
   }
 }
 
+// BatchNorm folded into the convolution that consumes it (no Dropout2d in between, no padding):
+//   conv(scale*y + shift; w, b) = conv(y; w * scale[c], b + sum_{t,c} w[k][t][c] * shift[c])
+// one block per output channel k of the packed operand [K][T][Cp]
+__global__ void __launch_bounds__(LT) bn_fold_weights_kernel(const void* w, int dtype, int T, int Cp, int C, const float* scale,
+                                                             const float* shift, const float* bias, void* w_out, float* bias_out) {
+  __shared__ float red[32];
+  const int k = blockIdx.x;
+  const int64_t base = (int64_t)k * T * Cp;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < T * Cp; i += LT) {
+    const int c = i % Cp;
+    float v = 0.f;
+    if (c < C) {
+      const float wv = icf::ld_any(w, dtype, base + i);
+      v = wv * scale[c];
+      s = fmaf(wv, shift[c], s);
+    }
+    icf::st_any(w_out, dtype, base + i, v);
+  }
+  const float t = icf::block_sum(s, red);
+  if (threadIdx.x == 0) bias_out[k] = (bias ? bias[k] : 0.f) + t;
+}
+
+// weight gradient of that convolution from the gradient computed against y:  dW[k][t][c] = G[k][t][c]*scale[c] + shift[c]*dbias[k]
+__global__ void __launch_bounds__(LT) bn_fold_wgrad_kernel(float* dw, int64_t total, int TC, int C, const float* scale,
+                                                           const float* shift, const float* dbias) {
+  for (int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x; i < total; i += (int64_t)gridDim.x * LT) {
+    const int c = (int)(i % C);
+    const int64_t k = i / TC;
+    dw[i] = fmaf(dw[i], scale[c], shift[c] * dbias[k]);
+  }
+}
+
 inline int grid_for(int64_t total) {
   int64_t b = (total + LT - 1) / LT;
   const int64_t cap = (int64_t)icf::sm_count() * 8;
@@ -168,6 +201,21 @@ int icf_scm_affine_cf(const icf_scm_affine_args* a, void* stream) {
   if (a->n == 0) return 0;
   scm_affine_cf_kernel<<<grid_for(a->n), LT, 0, icf::as_stream(stream)>>>(*a);
   return icf::check_launch("scm_affine_cf");
+}
+
+int icf_bn_fold_weights(const void* w, int32_t dtype, int32_t K, int32_t T, int32_t Cp, int32_t C, const float* scale,
+                        const float* shift, const float* bias, void* w_out, float* bias_out, void* stream) {
+  ICF_REQUIRE(w && w_out && bias_out && scale && shift && K > 0 && T > 0 && Cp >= C && C > 0, "icf_bn_fold_weights: bad arguments");
+  bn_fold_weights_kernel<<<K, LT, 0, icf::as_stream(stream)>>>(w, dtype, T, Cp, C, scale, shift, bias, w_out, bias_out);
+  return icf::check_launch("bn_fold_weights");
+}
+
+int icf_bn_fold_wgrad(float* dw, int32_t K, int32_t T, int32_t C, const float* scale, const float* shift, const float* dbias,
+                      void* stream) {
+  ICF_REQUIRE(dw && scale && shift && dbias && K > 0 && T > 0 && C > 0, "icf_bn_fold_wgrad: bad arguments");
+  const int64_t total = (int64_t)K * T * C;
+  bn_fold_wgrad_kernel<<<grid_for(total), LT, 0, icf::as_stream(stream)>>>(dw, total, T * C, C, scale, shift, dbias);
+  return icf::check_launch("bn_fold_wgrad");
 }
 
 int icf_onehot_swap(const void* idx, int32_t idx_is_int64, const uint8_t* mask, int64_t n, int32_t K, float* rows, void* stream) {

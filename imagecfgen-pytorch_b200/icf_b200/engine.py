@@ -137,6 +137,10 @@ class LayerExec:
         if self.px8:
             self.perm_px8_g = ops.make_perm4(C_, self.R, self.S, 1, self.R * self.S, self.S, 1, self.R * self.S, 8, self.S * 8)
             self.wgrad_elems = max(self.wgrad_elems, C_ * self.R * self.S * 8)
+        # BatchNorm folding (set by Tower): operand copy / bias of this layer with the preceding BatchNorm's scale / shift
+        # folded in, rebuilt per forward from the batch statistics
+        self.w_bnfold = None
+        self.bias_bnfold = None
         # algorithmic bytes per image (each tensor touched once, real channels — not the folded / padded operand widths)
         self.alg_bytes_img = 2.0 * (hin * win * self.Cin + self.Hout * self.Wout * self.Cout)
         self.alg_flops_img = 2.0 * self.Cin * self.Kout * ops.valid_taps(self.form, hin, self.P, self.R, self.stride, self.pad) \
@@ -165,7 +169,9 @@ class LayerExec:
             (ops.pack4 if isinstance(perm, Perm4) else ops.pack)(src, dst, dt, perm)
 
     # ---- launches -------------------------------------------------------------------------------
-    def forward(self, N, x: Act, y: Act, mask=None, mask_pitch=0, stats=None, out_f32=False):
+    def forward(self, N, x: Act, y: Act, mask=None, mask_pitch=0, stats=None, out_f32=False, w_override=None,
+                bias_override=None):
+        """``w_override`` / ``bias_override``: device addresses of a BatchNorm-folded operand copy / bias (see NetExec._tower_fwd)."""
         sp = self.spec
         if self.fold:      # x is the pre-padded [N][Hin+2p][Win+2p][8] feature tensor
             ops.conv_forward(self.code, self.form, N, self.Hin + 2 * self.pad, self.Win + 2 * self.pad,
@@ -183,9 +189,10 @@ class LayerExec:
             return
         ops.conv_forward(self.code, self.form, N, self.Hin, self.Win, self.Cin, x.pitch,
                          self.P, self.Q, self.Kout, y.pitch if sp.kind != "linear" else y.pitch * self.Hout * self.Wout,
-                         self.R, self.S, self.stride, self.pad, x.ptr, self.w_fwd.data_ptr(), self.Kout,
-                         self.wf_pitch, y.ptr, bias=self.bias.data_ptr(), act=sp.act, slope=sp.slope,
-                         out_f32=out_f32, mask=mask, mask_pitch=mask_pitch, stats=stats)
+                         self.R, self.S, self.stride, self.pad, x.ptr,
+                         self.w_fwd.data_ptr() if w_override is None else w_override, self.Kout,
+                         self.wf_pitch, y.ptr, bias=self.bias.data_ptr() if bias_override is None else bias_override,
+                         act=sp.act, slope=sp.slope, out_f32=out_f32, mask=mask, mask_pitch=mask_pitch, stats=stats)
 
     def dgrad(self, N, dpre: Act, dx: Act):
         """dx[n,h,w,c] = sum_{k,taps} dpre[...]*w  — the other conv form with the transposed operand."""
@@ -291,6 +298,20 @@ class Tower:
             h, w = le.Hout, le.Wout
         self.Hout, self.Wout = h, w
         self.code, self.device = code, device
+        # BatchNorm -> Conv2d with nothing in between (no Dropout2d after the BatchNorm) and no padding in the consumer:
+        # the affine transform folds into the consumer's weights and bias, the normalised tensor is never written
+        # (mnist.py:111-112, dx.4 -> dx.5).  ICF_NO_BN_FOLD=1 keeps the separate pass (tuning / bisecting aid).
+        self.bn_fold = {}
+        import os
+        if not os.environ.get("ICF_NO_BN_FOLD"):
+            for i in range(len(self.layers) - 1):
+                a, b = self.layers[i], self.layers[i + 1]
+                if (a.spec.bn and not a.spec.bn_drop and b.spec.kind == "conv" and b.pad == 0 and not b.fold
+                        and not b.gemm_fwd and not b.spec.in_drop):
+                    dt = ops.torch_dtype(code)
+                    b.w_bnfold = torch.zeros_like(b.w_fwd)
+                    b.bias_bnfold = torch.zeros(b.Kout, dtype=torch.float32, device=device)
+                    self.bn_fold[i] = i + 1
         # BatchNorm statistic accumulators, zero between uses (icf_bn_finalize clears them)
         self.stats = {i: torch.zeros(2 * le.Kout, dtype=torch.float32, device=device)
                       for i, le in enumerate(self.layers) if le.spec.bn}
@@ -401,6 +422,7 @@ class NetExec:
         ts = self.tensors()
         saved = []
         n_layers = len(tw.layers)
+        folded_ss = None
         for i, le in enumerate(tw.layers):
             sp = le.spec
             last = i == n_layers - 1
@@ -418,9 +440,18 @@ class NetExec:
                 om, om_ptr, om_pitch = fm, ops.ptr(fm, fm_off), fm.shape[1]
             use_stats = sp.bn is not None and training
             stats = tw.stats[i].data_ptr() if use_stats else None
+            wo = bo = None
+            if folded_ss is not None:            # the BatchNorm in front of this layer lives in its operand copy and bias
+                K_prev = le.Cin
+                ops.bn_fold_weights(le.w_fwd.data_ptr(), self.code, le.Kout, le.taps, le.wf_pitch, le.Cin, ops.ptr(folded_ss),
+                                    ops.ptr(folded_ss, K_prev), le.bias.data_ptr(), le.w_bnfold.data_ptr(),
+                                    le.bias_bnfold.data_ptr())
+                wo, bo = le.w_bnfold.data_ptr(), le.bias_bnfold.data_ptr()
             le.forward(N, x, y, mask=om_ptr, mask_pitch=om_pitch, stats=stats,
-                       out_f32=(y.t.dtype == torch.float32 and self.code == BF16))
-            rec = {"x": x, "y": y, "out_mask": (om, om_ptr, om_pitch) if om is not None else None, "bn": None}
+                       out_f32=(y.t.dtype == torch.float32 and self.code == BF16), w_override=wo, bias_override=bo)
+            rec = {"x": x, "y": y, "out_mask": (om, om_ptr, om_pitch) if om is not None else None, "bn": None,
+                   "in_fold": folded_ss}
+            folded_ss = None
             nxt = y
             if sp.bn is not None:
                 K = le.Kout
@@ -444,12 +475,16 @@ class NetExec:
                     ss[2 * K:3 * K] = rm
                     ss[3 * K:] = inv
                 bm = masks.get((i, "bn"))
-                u = Act(torch.empty((pix, y.pitch), dtype=self.dt, device=self.device), le.Cout)
-                ops.scale_shift_mask(y.ptr, y.code, y.pitch, u.ptr, u.code, u.pitch, pix, le.Hout * le.Wout, K,
-                                     scale=ops.ptr(ss), shift=ops.ptr(ss, K), mask=ops.ptr(bm),
-                                     mask_pitch=bm.shape[1] if bm is not None else 0)
+                if i in tw.bn_fold and bm is None:
+                    folded_ss = ss                     # consumed by the next layer's operand copy: no pass over y
+                    nxt = y
+                else:
+                    u = Act(torch.empty((pix, y.pitch), dtype=self.dt, device=self.device), le.Cout)
+                    ops.scale_shift_mask(y.ptr, y.code, y.pitch, u.ptr, u.code, u.pitch, pix, le.Hout * le.Wout, K,
+                                         scale=ops.ptr(ss), shift=ops.ptr(ss, K), mask=ops.ptr(bm),
+                                         mask_pitch=bm.shape[1] if bm is not None else 0)
+                    nxt = u
                 rec["bn"] = {"ss": ss, "mask": bm, "training": training}
-                nxt = u
             if save:
                 saved.append(rec)
             x = nxt
@@ -517,6 +552,10 @@ class NetExec:
                 if le.perm_bias is not None:
                     ops.unpack(dbias_t.data_ptr(), grads[sp.key + ".bias"].data_ptr(), le.perm_bias)
                 le.wgrad(N, dpre, x, None, self.wgrad_scratch(le))
+                fs = rec.get("in_fold")
+                if fs is not None:                 # gradient was taken against the un-normalised input: dW = G*scale + shift*dbias
+                    ops.bn_fold_wgrad(self.wgrad_scratch(le).data_ptr(), le.Kout, le.taps, le.Cin, ops.ptr(fs),
+                                      ops.ptr(fs, le.Cin), dbias)
             if i > 0 or need_dx:
                 dx = Act(torch.empty((N * le.Hin * le.Win, x.pitch), dtype=self.dt, device=self.device), le.Cin)
                 le.dgrad(N, dpre, dx)

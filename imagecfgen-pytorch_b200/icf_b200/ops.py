@@ -308,3 +308,11 @@ def onehot_swap(idx: torch.Tensor, mask, rows: torch.Tensor):
     _launch("icf_onehot_swap", _l.load().icf_onehot_swap, idx.contiguous().data_ptr(), 1 if idx.dtype == torch.int64 else 0,
             ptr(m), n, k, rows.data_ptr())
     return rows
+
+
+def bn_fold_weights(w, dtype, K, T, Cp, Cc, scale, shift, bias, w_out, bias_out):
+    _launch("icf_bn_fold_weights", _l.load().icf_bn_fold_weights, w, dtype, K, T, Cp, Cc, scale, shift, bias, w_out, bias_out)
+
+
+def bn_fold_wgrad(dw, K, T, Cc, scale, shift, dbias):
+    _launch("icf_bn_fold_wgrad", _l.load().icf_bn_fold_wgrad, dw, K, T, Cc, scale, shift, dbias)

@@ -228,6 +228,16 @@ int icf_scale_shift_mask(const void* y, int32_t y_dtype, int32_t y_pitch, void* 
                          int32_t u_pitch, int64_t pixels, int32_t pixels_per_sample, int32_t C,
                          const float* scale, const float* shift, const float* mask, int32_t mask_pitch,
                          void* stream);
+/* BatchNorm folded into the convolution that consumes its output when no Dropout2d sits in between and the convolution has no
+ * padding (mnist.py:111-112: BatchNorm2d(32) -> Conv2d(32,64,4,2)): the normalised tensor is never materialised.
+ *   forward   conv(scale*y + shift; w, b) = conv(y; w', b'),  w'[k][t][c] = w[k][t][c]*scale[c],  b'[k] = b[k] + sum_{t,c} w*shift[c]
+ *             (w, w_out: packed operands [K][T][Cp]; scale/shift as written by icf_bn_finalize)
+ *   backward  the data gradient uses the un-folded operand; the weight gradient G computed against y becomes
+ *             dW[k][t][c] = G[k][t][c]*scale[c] + shift[c]*dbias[k]   (dw: packed fp32 accumulator [K][T][C], in place) */
+int icf_bn_fold_weights(const void* w, int32_t dtype, int32_t K, int32_t T, int32_t Cp, int32_t C, const float* scale,
+                        const float* shift, const float* bias, void* w_out, float* bias_out, void* stream);
+int icf_bn_fold_wgrad(float* dw, int32_t K, int32_t T, int32_t C, const float* scale, const float* shift, const float* dbias,
+                      void* stream);
 /* sums[0][c] = sum du, sums[1][c] = sum du * xhat, du = dU*mask, xhat = (y-mean)*invstd  (+=) */
 int icf_bn_bwd_reduce(const void* dU, int32_t d_dtype, int32_t d_pitch, const void* y, int32_t y_dtype,
                       int32_t y_pitch, int64_t pixels, int32_t pixels_per_sample, int32_t C,

@@ -196,3 +196,46 @@ def test_counterfactual_pipeline_device_resident(dtype):
     _, c2_cf = synth.mnist_scale(x2, synth.intervene_mnist(a2, 2.0), stats)
     out2 = pipe.replay(im2.to(DEV), to_dev(a2))
     assert rel_err(out2, R.counterfactual(fam, sds["E"], sds["G"], im2, c2, c2_cf)) < tol
+
+
+def test_explainer_style_search_through_generator():
+    """Row N3 at the boundary: the gradient-based counterfactual search of explain/cf_example.py:107-168 (Adam over soft attribute
+    logits and tanh(z), autograd THROUGH G w.r.t. z and every attribute, G's weights frozen) runs on the engine's Generator and
+    follows the same loss trajectory as the oracle's functional G on the CPU.  The classifier is a fixed linear stand-in (the
+    reference's classifiers are outside the hot path)."""
+    fam, seed, std = "mnist", 25, 0.05
+    images, c, z, _ = golden_inputs(fam, 1, seed)
+    sdG = R.synth_state_dict(fam, "G", seed, std)
+    G = build(fam, seed, std, "fp32", "G")["G"]
+    G.requires_grad_(False)
+    gen = torch.Generator().manual_seed(1)
+    Wc = 0.05 * torch.randn(784, 10, generator=gen)
+    init = {"digit": 0.01 * torch.randn(1, 10, generator=gen), "thickness": 0.01 * torch.randn(1, 1, generator=gen),
+            "intensity": 0.01 * torch.randn(1, 1, generator=gen), "slant": 0.01 * torch.randn(1, 1, generator=gen),
+            "z": torch.randn(1, 512, 1, 1, generator=gen)}
+    target = 3
+
+    def run(dev, decode):
+        params = {k: v.clone().to(dev).requires_grad_(True) for k, v in init.items()}
+        opt = torch.optim.Adam(list(params.values()), lr=0.1)
+        x, W = images.to(dev), Wc.to(dev)
+        losses = []
+        for _ in range(6):
+            opt.zero_grad()
+            attrs = {k: (params[k].softmax(1) if k == "digit" else params[k].tanh()) for k in params if k != "z"}
+            x_cf = decode(params["z"].tanh(), attrs)
+            pred = x_cf.reshape(1, -1) @ W
+            others = torch.cat([pred[:, :target], pred[:, target + 1:]], 1).max()
+            loss = 10.0 * (others - pred[:, target]).mean() + (x - x_cf).abs().mean()
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        return losses, {k: v.detach().cpu() for k, v in params.items()}
+
+    want, p_ref = run("cpu", lambda zz, a: R.generator_fwd(fam, sdG, zz, a))
+    got, p_got = run(DEV, lambda zz, a: G(zz, a))
+    print(got, want)
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 1e-3 * max(abs(b), 0.1), (got, want)
+    for k in p_ref:
+        assert rel_err(p_got[k], p_ref[k]) < 2e-3, k
