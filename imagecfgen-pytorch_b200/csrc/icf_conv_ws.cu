@@ -37,7 +37,8 @@ constexpr int WS_THREADS = WS_EPI0 + 128 * WS_EPI_GROUPS;
 constexpr int WS_MAX_CLASSES = 4, WS_MAX_TAPS = 25, WS_MAX_SUBS = 2, WS_MAX_ACC = 16, WS_MAX_SLOTS = 8;
 constexpr int WS_SMEM_BUDGET = 220 * 1024;
 constexpr int WS_MAX_GROUPS = 8;
-constexpr int WS_PROG_WORDS = 1536;                 // issuer schedules of all classes (4-byte actions), in the kernel parameters
+constexpr int WS_PROG_WORDS = 4096;                 // issuer schedules of all classes (4-byte actions), in the kernel parameters
+                                                    // (one to two words per source row and issuer: 512-row images need ~2400)
 
 struct WsTap {
   int16_t dy;        // source row = i*sstep + dy
@@ -568,7 +569,10 @@ int ws_forward_impl(const icf_conv_args* a, cudaStream_t st, int32_t* plan, int3
   // ---- column shape: XG output x positions times NG images ----
   double best = 1e30;
   for (int xg = 1; xg <= 16; xg *= 2) {
-    const double eff = (double)max_q / (icf::cdiv(max_q, xg) * xg);
+    // useful MMA rows of a column: x positions inside the row times images inside the batch (a column is XG x positions of
+    // NG = 128/XG images — with 32 images per step a 1 x 128 column would be three quarters padding)
+    const int ng = 128 / xg;
+    const double eff = (double)max_q / (icf::cdiv(max_q, xg) * xg) * ((double)a->N / ((double)icf::cdiv(a->N, ng) * ng));
     // wasted MMA rows (1/eff) against x-halo re-fetch; stride-2 gathers load two parity sub-rows per source row and
     // measured better with wide columns (G.layers.6 dgrad: XG 16 beats XG 2 by 25 %)
     const double cost = (1.0 / eff) * (1.0 + (q.sstep == 2 ? 0.5 : 0.25) * brange / xg);

@@ -127,6 +127,89 @@ __global__ void __launch_bounds__(LT) onehot_swap_kernel(const void* idx, int id
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// "Taps as channels": a stride-s transposed convolution with very few output channels (the generator's single-channel
+// tail ConvTranspose2d(C, 1, 5, 2, 2, 1), the data gradient of the first encoder / discriminator conv towards the
+// attribute-plane channels) is a plain GEMM over the INPUT pixels,  T[pixel][(k, tap)] = sum_c in[pixel][c] * w[k][tap][c]
+// (N = K*R*S columns on the tensor cores, every input element read once), followed by a col2im gather
+//   out[n][oy][ox][k] = act(bias[k] + sum_{taps whose (oy+pad-r, ox+pad-s) is a multiple of the stride} T[...]) .
+// The gather form of the same layers (one MMA chain per output-parity class and tap with N = 16 for 1-3 useful columns)
+// is issue-bound at 4-6 % of the HBM roofline (profiles/r02_per_layer_esrf_acoustic.json).
+// The mirror image for a conv whose INPUT has one channel (data / weight gradient of that tail): im2col of the single
+// plane into [pixel][tap] rows, then plain GEMMs.
+// ------------------------------------------------------------------------------------------------------------------
+// col2im: T [N*H*W][t_pitch] (columns k*TP + tap, TP = tap stride) -> out [N*P*Q][out_pitch] channels 0..K-1
+// one block row per output row (n, oy): the filter rows that reach it are resolved once per block, threads walk ox
+template <int KMAX>
+__global__ void __launch_bounds__(LT) col2im_taps_kernel(const __nv_bfloat16* __restrict__ T, int t_pitch, int TP, int H, int W,
+                                                         int P, int Q, int K, int R, int S, int stride, int pad,
+                                                         const float* bias, int act, float slope, void* out, int out_dtype,
+                                                         int out_pitch) {
+  const int row = blockIdx.x;                       // n*P + oy
+  const int n = row / P, oy = row - n * P;
+  // filter rows r = ry0, ry0 + stride, ... with iy = (oy + pad - r)/stride inside the input
+  int ry[4], iyv[4], nry = 0;
+  for (int r = (oy + pad) % stride; r < R && nry < 4; r += stride) {
+    const int d = oy + pad - r;
+    if (d >= 0 && d / stride < H) { ry[nry] = r; iyv[nry] = d / stride; ++nry; }
+  }
+  for (int ox = blockIdx.y * LT + threadIdx.x; ox < Q; ox += gridDim.y * LT) {
+    float acc[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) acc[k] = (bias && k < K) ? bias[k] : 0.f;
+    for (int sx = (ox + pad) % stride; sx < S; sx += stride) {
+      const int d = ox + pad - sx;
+      if (d < 0) break;                             // larger sx only moves further left
+      const int ix = d / stride;
+      if (ix >= W) continue;
+      for (int j = 0; j < nry; ++j) {
+        const __nv_bfloat16* t = T + (((int64_t)n * H + iyv[j]) * W + ix) * t_pitch + ry[j] * S + sx;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k < K) acc[k] += __bfloat162float(t[k * TP]);
+      }
+    }
+    const int64_t o = (int64_t)row * Q + ox;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) icf::st_any(out, out_dtype, o * out_pitch + k, icf::apply_act(acc[k], act, slope));
+  }
+}
+
+// im2col of channel 0 of src [N*P*Q][src_pitch] into A [N*H*W][a_pitch]: A[n,iy,ix][r*S+s] = src[n, iy*stride-pad+r, ix*stride-pad+s]
+// (zero outside, zero in the padding columns R*S .. a_pitch-1); one thread per (pixel, 8-column group) -> 16-byte stores
+__global__ void __launch_bounds__(LT) im2col_taps_kernel(const void* src, int src_dtype, int src_pitch, int N, int P, int Q, int H, int W,
+                                                         int R, int S, int stride, int pad, __nv_bfloat16* A, int a_pitch) {
+  const int groups = a_pitch >> 3;
+  const int64_t total = (int64_t)N * H * W * groups;
+  for (int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x; i < total; i += (int64_t)gridDim.x * LT) {
+    const int g = (int)(i % groups);
+    const int64_t pix = i / groups;
+    const int ix = (int)(pix % W);
+    const int64_t t1 = pix / W;
+    const int iy = (int)(t1 % H);
+    const int n = (int)(t1 / H);
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      float v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int t = g * 8 + j + h;
+        v[h] = 0.f;
+        if (t < R * S) {
+          const int r = t / S, sx = t - r * S;
+          const int y = iy * stride - pad + r, x = ix * stride - pad + sx;
+          if (y >= 0 && y < P && x >= 0 && x < Q) v[h] = icf::ld_any(src, src_dtype, (((int64_t)n * P + y) * Q + x) * src_pitch);
+        }
+      }
+      __nv_bfloat162 pk = __floats2bfloat162_rn(v[0], v[1]);
+      w[j >> 1] = *reinterpret_cast<uint32_t*>(&pk);
+    }
+    *reinterpret_cast<uint4*>(A + pix * a_pitch + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 // BatchNorm folded into the convolution that consumes it (no Dropout2d in between, no padding):
 //   conv(scale*y + shift; w, b) = conv(y; w * scale[c], b + sum_{t,c} w[k][t][c] * shift[c])
 // one block per output channel k of the packed operand [K][T][Cp]
@@ -201,6 +284,39 @@ int icf_scm_affine_cf(const icf_scm_affine_args* a, void* stream) {
   if (a->n == 0) return 0;
   scm_affine_cf_kernel<<<grid_for(a->n), LT, 0, icf::as_stream(stream)>>>(*a);
   return icf::check_launch("scm_affine_cf");
+}
+
+int icf_col2im_taps(const void* T, int32_t t_pitch, int32_t TP, int32_t N, int32_t H, int32_t W, int32_t P, int32_t Q, int32_t K,
+                    int32_t R, int32_t S, int32_t stride, int32_t pad, const float* bias, int32_t act, float slope, void* out,
+                    int32_t out_dtype, int32_t out_pitch, void* stream) {
+  ICF_REQUIRE(T && out && N >= 0 && H > 0 && W > 0 && P > 0 && Q > 0 && K > 0 && R > 0 && S > 0 && stride > 0 && pad >= 0 &&
+                  TP >= R * S && t_pitch >= K * TP && out_pitch >= K,
+              "icf_col2im_taps: bad arguments");
+  if (N == 0) return 0;
+  ICF_REQUIRE(K <= 8 && (R + stride - 1) / stride <= 4 && (int64_t)N * P < 0x7fffffffLL, "icf_col2im_taps: at most 8 channels, 4 rows per parity");
+  const dim3 grid((unsigned)(N * P), (unsigned)((Q + LT - 1) / LT));
+  const __nv_bfloat16* Tb = reinterpret_cast<const __nv_bfloat16*>(T);
+  if (K == 1)
+    col2im_taps_kernel<1><<<grid, LT, 0, icf::as_stream(stream)>>>(Tb, t_pitch, TP, H, W, P, Q, K, R, S, stride, pad, bias, act, slope,
+                                                                   out, out_dtype, out_pitch);
+  else if (K <= 2)
+    col2im_taps_kernel<2><<<grid, LT, 0, icf::as_stream(stream)>>>(Tb, t_pitch, TP, H, W, P, Q, K, R, S, stride, pad, bias, act, slope,
+                                                                   out, out_dtype, out_pitch);
+  else
+    col2im_taps_kernel<8><<<grid, LT, 0, icf::as_stream(stream)>>>(Tb, t_pitch, TP, H, W, P, Q, K, R, S, stride, pad, bias, act, slope,
+                                                                   out, out_dtype, out_pitch);
+  return icf::check_launch("col2im_taps");
+}
+
+int icf_im2col_taps(const void* src, int32_t src_dtype, int32_t src_pitch, int32_t N, int32_t P, int32_t Q, int32_t H, int32_t W,
+                    int32_t R, int32_t S, int32_t stride, int32_t pad, void* A, int32_t a_pitch, void* stream) {
+  ICF_REQUIRE(src && A && N >= 0 && P > 0 && Q > 0 && H > 0 && W > 0 && R > 0 && S > 0 && stride > 0 && pad >= 0 &&
+                  a_pitch >= R * S && (a_pitch & 7) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0,
+              "icf_im2col_taps: bad arguments");
+  if (N == 0) return 0;
+  im2col_taps_kernel<<<grid_for((int64_t)N * H * W * (a_pitch >> 3)), LT, 0, icf::as_stream(stream)>>>(
+      src, src_dtype, src_pitch, N, P, Q, H, W, R, S, stride, pad, reinterpret_cast<__nv_bfloat16*>(A), a_pitch);
+  return icf::check_launch("im2col_taps");
 }
 
 int icf_bn_fold_weights(const void* w, int32_t dtype, int32_t K, int32_t T, int32_t Cp, int32_t C, const float* scale,

@@ -137,6 +137,27 @@ class LayerExec:
         if self.px8:
             self.perm_px8_g = ops.make_perm4(C_, self.R, self.S, 1, self.R * self.S, self.S, 1, self.R * self.S, 8, self.S * 8)
             self.wgrad_elems = max(self.wgrad_elems, C_ * self.R * self.S * 8)
+        # "Taps as channels" (icf.h, icf_col2im_taps / icf_im2col_taps): stride-2 layers with one channel on one side run as
+        # plain GEMMs over the pixels with the filter taps as the other dimension.
+        #  tail: ConvTranspose2d(C, 1, k, 2, ...) — forward = GEMM [pix, C] x [C, taps] + col2im (+bias, tanh); data gradient =
+        #        im2col of the one-channel gradient + GEMM [pix, taps] x [taps, C]; weight gradient = GEMM-wgrad X^T x im2col
+        #  head: the data gradient of a first Conv2d(<= 8 channels, K, k, 2, ...) = GEMM [pix, K] x [K, C*taps] + col2im
+        import os as _os
+        _off = bool(_os.environ.get("ICF_NO_TAPS"))
+        self.tail_taps = (not _off and spec.kind == "convT" and code == BF16 and self.Kout == 1 and self.stride == 2
+                          and self.Cin % 8 == 0 and self.taps <= 32 and not self.px8)
+        self.head_ok = (not _off and spec.kind == "conv" and code == BF16 and self.stride == 2 and self.Cin <= 8
+                        and self.Kout % 8 == 0 and self.taps <= 32)
+        self.head_taps = False                    # enabled by NetExec.enable_head_taps for the attribute-plane channels
+        self.head_active = False
+        self._im2col = None                       # (key of the gradient tensor, its im2col matrix): shared by wgrad and dgrad
+        if self.tail_taps:
+            self.TP = pad8(self.taps)
+            self.w_tail_f = torch.zeros(self.TP * self.wf_pitch, dtype=dt, device=device)       # [taps][1][C]
+            self.perm_tail_f = ops.make_perm(T, 1, C_, 1, 0, T, d2_pad=self.wf_pitch, d0_pad=self.TP)
+            self.w_tail_b = torch.zeros(C_ * self.TP, dtype=dt, device=device)                  # [C][1][taps]
+            self.perm_tail_b = ops.make_perm(C_, 1, T, T, 0, 1, d2_pad=self.TP)
+            self.perm_tail_g = ops.make_perm(C_, 1, T, T, 0, 1)                                 # dw packed [C][1][taps] = checkpoint order
         # BatchNorm folding (set by Tower): operand copy / bias of this layer with the preceding BatchNorm's scale / shift
         # folded in, rebuilt per forward from the batch statistics
         self.w_bnfold = None
@@ -147,6 +168,22 @@ class LayerExec:
             * ops.valid_taps(self.form, win, self.Q, self.S, self.stride, self.pad)
 
     # ---- operands -------------------------------------------------------------------------------
+    def enable_head_taps(self, c_lo: int, c_hi: int):
+        """The data gradient of this first conv is only ever needed for input channels [c_lo, c_hi) (the embedded attribute
+        planes: the image and the constant planes are data).  With one or two such channels it runs as
+        GEMM [out pixel, K] x [K, (c, tap)] + col2im instead of the gather form's N = 16 MMA chains per parity class and tap."""
+        if not self.head_ok or c_hi - c_lo < 1 or c_hi - c_lo > 2:
+            return
+        T = self.taps
+        self.head_lo, self.head_n = c_lo, c_hi - c_lo
+        self.head_rows = self.head_n * T                                                    # T columns (c, tap)
+        self.head_cols = pad8(self.head_rows)
+        dt = ops.torch_dtype(self.code)
+        self.w_head = torch.zeros(self.head_cols * self.wb_pitch, dtype=dt, device=self.device)   # [(c,tap)][1][K]
+        self.perm_head = ops.make_perm(self.head_rows, 1, self.Kout, 1, 0, self.Cin * T, d2_pad=self.wb_pitch,
+                                       d0_pad=self.head_cols)
+        self.head_taps = True
+
     def pack_jobs(self, weight: torch.Tensor, bias: torch.Tensor):
         """[(src ptr, dst ptr, dst dtype, perm)] that refresh this layer's operand copies from its parameters."""
         wp, bp = weight.data_ptr(), bias.data_ptr()
@@ -160,6 +197,11 @@ class LayerExec:
         if self.gemm_fwd:
             jobs.append((wp, self.w_gemm.data_ptr(), self.code, self.perm_gemm))
             jobs.append((bp, self.bias_gemm.data_ptr(), F32, self.perm_bias_gemm))
+        if self.tail_taps:
+            jobs.append((wp, self.w_tail_f.data_ptr(), self.code, self.perm_tail_f))
+            jobs.append((wp, self.w_tail_b.data_ptr(), self.code, self.perm_tail_b))
+        if self.head_taps:      # rows (c, tap) of channels head_lo .. : the source starts head_lo*taps floats into each k-slab
+            jobs.append((wp + 4 * self.head_lo * self.taps, self.w_head.data_ptr(), self.code, self.perm_head))
         return jobs
 
     def repack(self, weight: torch.Tensor, bias: torch.Tensor):
@@ -181,6 +223,15 @@ class LayerExec:
                              win=self.fold, alg_flops=self.alg_flops_img * N,
                              alg_bytes=self.alg_bytes_img * N + 2.0 * self.wgrad_elems)
             return
+        if self.tail_taps and mask is None and stats is None and w_override is None:
+            # T[pixel][tap] = x[pixel][:] . w[:, tap]  (plain GEMM over the input pixels), then col2im + bias + activation
+            Tm = torch.empty((N * self.Hin * self.Win, self.TP), dtype=ops.torch_dtype(self.code), device=self.device)
+            ops.conv_forward(self.code, ops.GATHER, N, self.Hin, self.Win, self.Cin, x.pitch, self.Hin, self.Win, self.taps,
+                             self.TP, 1, 1, 1, 0, x.ptr, self.w_tail_f.data_ptr(), self.TP, self.wf_pitch, Tm.data_ptr(),
+                             alg_flops=self.alg_flops_img * N, alg_bytes=self.alg_bytes_img * N)
+            ops.col2im_taps(Tm.data_ptr(), self.TP, self.TP, N, self.Hin, self.Win, self.P, self.Q, 1, self.R, self.S,
+                            self.stride, self.pad, self.bias.data_ptr(), sp.act, sp.slope, y.ptr, y.code, y.pitch)
+            return
         if self.gemm_fwd and mask is None and stats is None and y.pitch == self.Kout and y.off == 0:
             ops.conv_forward(self.code, ops.GATHER, N, 1, 1, self.Cin, x.pitch, 1, 1, self.taps * self.Kout,
                              y.pitch * self.taps, 1, 1, 1, 0, x.ptr, self.w_gemm.data_ptr(), self.taps * self.Kout,
@@ -196,6 +247,23 @@ class LayerExec:
 
     def dgrad(self, N, dpre: Act, dx: Act):
         """dx[n,h,w,c] = sum_{k,taps} dpre[...]*w  — the other conv form with the transposed operand."""
+        if self.tail_taps:
+            A = self._im2col_of(N, dpre, consume=True)
+            ops.conv_forward(self.code, ops.GATHER, N, self.Hin, self.Win, self.taps, self.TP, self.Hin, self.Win, self.Cin,
+                             dx.pitch, 1, 1, 1, 0, A.data_ptr(), self.w_tail_b.data_ptr(), self.Cin, self.TP, dx.ptr,
+                             alg_flops=self.alg_flops_img * N, alg_bytes=self.alg_bytes_img * N)
+            return
+        if self.head_taps and self.head_active:
+            # dX towards the attribute-plane channels only: T[out pixel][(c, tap)] = dpre[out pixel][:] . w[:, c, tap], then col2im
+            Tm = torch.empty((N * self.P * self.Q, self.head_cols), dtype=ops.torch_dtype(self.code), device=self.device)
+            ops.conv_forward(self.code, ops.GATHER, N, self.P, self.Q, self.Kout, dpre.pitch, self.P, self.Q, self.head_rows,
+                             self.head_cols, 1, 1, 1, 0, dpre.ptr, self.w_head.data_ptr(), self.head_cols, self.wb_pitch,
+                             Tm.data_ptr(), alg_flops=self.alg_flops_img * N * self.head_n / self.Cin,
+                             alg_bytes=2.0 * N * (self.P * self.Q * self.Kout + self.Hin * self.Win * self.head_n))
+            ops.col2im_taps(Tm.data_ptr(), self.head_cols, self.taps, N, self.P, self.Q, self.Hin, self.Win, self.head_n, self.R,
+                            self.S, self.stride, self.pad, None, "none", 0.0, ops.ptr(dx.t, dx.off + self.head_lo), dx.code,
+                            dx.pitch)
+            return
         form = ops.TRANSPOSED if self.form == ops.GATHER else ops.GATHER
         lin = self.spec.kind == "linear"
         dp_pitch = dpre.pitch * self.Hout * self.Wout if lin else dpre.pitch
@@ -203,8 +271,25 @@ class LayerExec:
                          self.Hin, self.Win, self.Cin, dx.pitch, self.R, self.S, self.stride, self.pad,
                          dpre.ptr, self.w_bwd.data_ptr(), self.Cin, self.wb_pitch, dx.ptr)
 
+    def _im2col_of(self, N, dpre: Act, consume: bool):
+        """[N*Hin*Win, TP] tap matrix of the one-channel gradient ``dpre``.  A backward pass calls wgrad, then dgrad, on the same
+        gradient tensor: wgrad always builds the matrix and leaves it for the dgrad that follows (``consume``), which drops it —
+        a matrix is never reused across backward passes (the allocator hands the same address to other contents)."""
+        key = (dpre.ptr, N)
+        if consume and self._im2col is not None and self._im2col[0] == key:
+            A = self._im2col[1]
+            self._im2col = None
+            return A
+        A = torch.empty((N * self.Hin * self.Win, self.TP), dtype=ops.torch_dtype(self.code), device=self.device)
+        ops.im2col_taps(dpre.ptr, dpre.code, dpre.pitch, N, self.P, self.Q, self.Hin, self.Win, self.R, self.S, self.stride,
+                        self.pad, A.data_ptr(), self.TP)
+        self._im2col = None if consume else (key, A)
+        return A
+
     def unpack_perm(self):
         """Permutation that takes this layer's packed fp32 weight-gradient accumulator to the checkpoint layout."""
+        if self.tail_taps:
+            return self.perm_tail_g
         if self.fold:
             return self.perm_fold_g
         if self.px8:
@@ -219,6 +304,10 @@ class LayerExec:
             self._wgrad_accumulate(N, dpre, x, scratch)
             return
         ops.fill_f32(scratch.data_ptr(), 0.0, n)
+        if self.tail_taps:
+            self._wgrad_accumulate(N, dpre, x, scratch)
+            ops.unpack(scratch.data_ptr(), gw.data_ptr(), self.perm_tail_g)
+            return
         if self.fold:
             ops.conv_wgrad(self.code, N, self.P, self.Q, self.Kout, dpre.pitch, self.Hin + 2 * self.pad,
                            self.Win + 2 * self.pad, self.fold * x.pitch, x.pitch, self.R, 1, self.stride, 0, dpre.ptr,
@@ -244,6 +333,12 @@ class LayerExec:
 
     def _wgrad_accumulate(self, N, dpre: Act, x: Act, scratch: torch.Tensor):
         """The wgrad launch alone: accumulates into the (already zeroed) packed fp32 buffer ``scratch``."""
+        if self.tail_taps:
+            A = self._im2col_of(N, dpre, consume=False)           # dw[c][tap] = sum_pixels x[pixel][c] * A[pixel][tap]
+            ops.conv_wgrad(self.code, N, self.Hin, self.Win, self.Cin, x.pitch, self.Hin, self.Win, self.taps, self.TP, 1, 1, 1,
+                           0, x.ptr, A.data_ptr(), scratch.data_ptr(), alg_flops=self.alg_flops_img * N,
+                           alg_bytes=self.alg_bytes_img * N + 4.0 * self.wgrad_elems)
+            return
         if self.fold:
             ops.conv_wgrad(self.code, N, self.P, self.Q, self.Kout, dpre.pitch, self.Hin + 2 * self.pad,
                            self.Win + 2 * self.pad, self.fold * x.pitch, x.pitch, self.R, 1, self.stride, 0, dpre.ptr,
@@ -338,6 +433,8 @@ class NetExec:
             self.towers = {"Dx": Tower(fam.Dx, H, W, code, device, fold_first=True), "Dz": Tower(fam.Dz, 1, 1, code, device),
                            "Dxz": Tower(fam.Dxz, 1, 1, code, device)}
             self.sites = mask_sites(fam)
+        if role in ("E", "D") and self.n_emb > 0:
+            self.towers["E" if role == "E" else "Dx"].layers[0].enable_head_taps(1, 1 + self.n_emb)
         self._versions = None
         self._pack_table = None
         self._pack_ptrs = None
@@ -665,6 +762,7 @@ class NetExec:
     def _encoder_backward(self, st, dout: Act, grads, need_dX=False):
         N = st["N"]
         need_feat = need_dX or (grads is not None and self.n_emb > 0)
+        self.towers["E"].layers[0].head_active = not need_dX          # only the attribute-plane channels of dfeat are read
         dfeat = self._tower_bwd("E", N, st["tower"], dout, grads, need_feat, inplace_ok=False)
         if dfeat is None:
             return None
@@ -782,6 +880,7 @@ class NetExec:
         dX = None
         if need_dX or grads is not None:
             need_feat = need_dX or (grads is not None and self.n_emb > 0)
+            self.towers["Dx"].layers[0].head_active = not need_dX
             dfeat = self._tower_bwd("Dx", N, st["Dx"], Act(dcat.t, kx, 0), grads, need_feat, inplace_ok=False)
             if dfeat is not None:
                 if grads is not None and self.n_emb > 0:

@@ -316,3 +316,15 @@ def bn_fold_weights(w, dtype, K, T, Cp, Cc, scale, shift, bias, w_out, bias_out)
 
 def bn_fold_wgrad(dw, K, T, Cc, scale, shift, dbias):
     _launch("icf_bn_fold_wgrad", _l.load().icf_bn_fold_wgrad, dw, K, T, Cc, scale, shift, dbias)
+
+
+def col2im_taps(T, t_pitch, TP, N, H, W, P, Q, K, R, S, stride, pad, bias, act, slope, out, out_dtype, out_pitch):
+    nb = 2.0 * N * H * W * t_pitch + (4.0 if out_dtype == F32 else 2.0) * N * P * Q * K
+    _launch("icf_col2im_taps", _l.load().icf_col2im_taps, T, t_pitch, TP, N, H, W, P, Q, K, R, S, stride, pad, bias, ACT[act],
+            slope, out, out_dtype, out_pitch, nbytes=nb, detail=f"col2im_taps {H}x{W}->{K}x{P}x{Q}" if PROFILE is not None else "")
+
+
+def im2col_taps(src, src_dtype, src_pitch, N, P, Q, H, W, R, S, stride, pad, A, a_pitch):
+    nb = 2.0 * N * H * W * a_pitch + (4.0 if src_dtype == F32 else 2.0) * N * P * Q
+    _launch("icf_im2col_taps", _l.load().icf_im2col_taps, src, src_dtype, src_pitch, N, P, Q, H, W, R, S, stride, pad, A, a_pitch,
+            nbytes=nb, detail=f"im2col_taps {P}x{Q}->{H}x{W}x{a_pitch}" if PROFILE is not None else "")

@@ -212,12 +212,15 @@ class BiGANTrainer:
             l, sD = exD.discriminator_forward(N, xp, xc, 1, zE.ptr, zE.code, zE.pitch, c, masks=masks6[2])
             ops.bce_logits(l.ptr, F32, 1, N, 1.0, 1.0, ops.ptr(out, 1), dl.data_ptr(), F32, 1)
             exD.discriminator_backward(sD, Act(dl, 1), self.gradsD)
-            self._allreduce(self.gD.grad)
+            evB = self._allreduce(self.gD.grad, side=True)
+            # ---- Phase C: discriminator on generated pairs (mnist.py:237-241) --------------------------
+            # G(z) of phase C does not depend on D: it runs while phase B's gradient all-reduce is in flight on the side stream
+            xG, _ = exG.generator_forward(N, zp, F32, fam.latent, c, save=False)
+            if evB is not None:
+                torch.cuda.current_stream().wait_event(evB)
             self._adam(self.gD, self.stateD)
             exD.repack(force=True)
-            # ---- Phase C: discriminator on generated pairs (mnist.py:237-241) --------------------------
             ops.fill_f32(self.gD.grad.data_ptr(), 0.0, self.gD.n)
-            xG, _ = exG.generator_forward(N, zp, F32, fam.latent, c, save=False)
             l, sD = exD.discriminator_forward(N, xG.ptr, xG.code, xG.pitch, zp, F32, fam.latent, c, masks=masks6[3])
             ops.bce_logits(l.ptr, F32, 1, N, 0.0, 1.0, ops.ptr(out, 2), dl.data_ptr(), F32, 1)
             exD.discriminator_backward(sD, Act(dl, 1), self.gradsD)

@@ -83,7 +83,7 @@ int icf_conv_forward(const icf_conv_args* a, void* stream);
 
 /* Introspection / test hook, no kernel launch and no GPU needed: the plan the weight-stationary row-streaming kernel
  * would use for `a` (pointers in `a` only need to be 16-byte aligned, they are not dereferenced).  Returns 0 and fills
- * `out`, -1 when the geometry is outside that kernel's envelope, > 0 on error.  `out` needs 16 + 4*48 + 1536 int32 words:
+ * `out`, -1 when the geometry is outside that kernel's envelope, > 0 on error.  `out` needs 16 + 4*48 + 4096 int32 words:
  *   [0] classes (output-parity classes of a transposed conv, else 1)  [1] XG  [2] NG  (a column = XG output columns x NG
  *   images = 128 MMA rows)  [3] ring slots  [4] TMEM accumulators  [5] channel tile  [6] source step  [7] output step
  *   [8] issuer warps  [9] schedule words in total  [10] grid  [11] channel tiles  [12] image groups  [13] schedule bytes in smem
@@ -228,6 +228,20 @@ int icf_scale_shift_mask(const void* y, int32_t y_dtype, int32_t y_pitch, void* 
                          int32_t u_pitch, int64_t pixels, int32_t pixels_per_sample, int32_t C,
                          const float* scale, const float* shift, const float* mask, int32_t mask_pitch,
                          void* stream);
+/* "Taps as channels" for the layers with ONE (or very few) channels on one side and a stride-2 5x5 filter — the generator tail
+ * ConvTranspose2d(C, 1, 5, 2, 2, 1) (audio_mnist.py:242, whalecalls.py:306, esrf_acoustic.py:197) and the data gradient of the
+ * first conv towards the attribute-plane channels: the contraction over the C channels runs as a plain 1x1 icf_conv_forward /
+ * icf_conv_wgrad GEMM whose other dimension are the filter taps, and these two kernels move between the tap-major matrix and
+ * the image:
+ *   icf_col2im_taps  out[n,oy,ox,k] = act(bias[k] + sum over taps (r,s) with (oy+pad-r, ox+pad-s) = stride*(iy,ix) of
+ *                    T[n,iy,ix][k*TP + r*S+s])            T: bf16 [N*H*W][t_pitch], TP = tap count padded
+ *   icf_im2col_taps  A[n,iy,ix][r*S+s] = src[n, iy*stride-pad+r, ix*stride-pad+s][0]  (zero outside / in the padding columns)
+ *                    A: bf16 [N*H*W][a_pitch], a_pitch a multiple of 8 */
+int icf_col2im_taps(const void* T, int32_t t_pitch, int32_t TP, int32_t N, int32_t H, int32_t W, int32_t P, int32_t Q, int32_t K,
+                    int32_t R, int32_t S, int32_t stride, int32_t pad, const float* bias, int32_t act, float slope, void* out,
+                    int32_t out_dtype, int32_t out_pitch, void* stream);
+int icf_im2col_taps(const void* src, int32_t src_dtype, int32_t src_pitch, int32_t N, int32_t P, int32_t Q, int32_t H, int32_t W,
+                    int32_t R, int32_t S, int32_t stride, int32_t pad, void* A, int32_t a_pitch, void* stream);
 /* BatchNorm folded into the convolution that consumes its output when no Dropout2d sits in between and the convolution has no
  * padding (mnist.py:111-112: BatchNorm2d(32) -> Conv2d(32,64,4,2)): the normalised tensor is never materialised.
  *   forward   conv(scale*y + shift; w, b) = conv(y; w', b'),  w'[k][t][c] = w[k][t][c]*scale[c],  b'[k] = b[k] + sum_{t,c} w*shift[c]

@@ -116,7 +116,7 @@ def test_flop_accounting_matches_survey():
 def _ws_plan(a):
     """(header, classes, schedule words) of the row-streaming kernel for ConvArgs `a`, or None if it declines."""
     from icf_b200 import lib
-    words = 16 + 4 * 48 + 1536
+    words = 16 + 4 * 48 + 4096
     out = (ctypes.c_int32 * words)()
     rc = lib.load().icf_ws_plan(ctypes.byref(a), out, words)
     if rc == -1:
