@@ -139,40 +139,40 @@ __global__ void __launch_bounds__(LT) onehot_swap_kernel(const void* idx, int id
 // plane into [pixel][tap] rows, then plain GEMMs.
 // ------------------------------------------------------------------------------------------------------------------
 // col2im: T [N*H*W][t_pitch] (columns k*TP + tap, TP = tap stride) -> out [N*P*Q][out_pitch] channels 0..K-1
-// one block row per output row (n, oy): the filter rows that reach it are resolved once per block, threads walk ox
+// one thread per output pixel (32-bit index arithmetic), at most 4 filter rows / columns reach a pixel
 template <int KMAX>
-__global__ void __launch_bounds__(LT) col2im_taps_kernel(const __nv_bfloat16* __restrict__ T, int t_pitch, int TP, int H, int W,
+__global__ void __launch_bounds__(LT) col2im_taps_kernel(const __nv_bfloat16* __restrict__ T, int t_pitch, int TP, int N, int H, int W,
                                                          int P, int Q, int K, int R, int S, int stride, int pad,
                                                          const float* bias, int act, float slope, void* out, int out_dtype,
                                                          int out_pitch) {
-  const int row = blockIdx.x;                       // n*P + oy
-  const int n = row / P, oy = row - n * P;
-  // filter rows r = ry0, ry0 + stride, ... with iy = (oy + pad - r)/stride inside the input
-  int ry[4], iyv[4], nry = 0;
-  for (int r = (oy + pad) % stride; r < R && nry < 4; r += stride) {
-    const int d = oy + pad - r;
-    if (d >= 0 && d / stride < H) { ry[nry] = r; iyv[nry] = d / stride; ++nry; }
-  }
-  for (int ox = blockIdx.y * LT + threadIdx.x; ox < Q; ox += gridDim.y * LT) {
+  const uint32_t rows = (uint32_t)N * (uint32_t)P;
+  const uint64_t total = (uint64_t)rows * (uint32_t)Q;
+  for (uint64_t o = (uint64_t)blockIdx.x * LT + threadIdx.x; o < total; o += (uint64_t)gridDim.x * LT) {
+    const uint32_t row = (uint32_t)(o / (uint32_t)Q);
+    const int ox = (int)(o - (uint64_t)row * (uint32_t)Q);
+    const int n = (int)(row / (uint32_t)P), oy = (int)(row - (uint32_t)n * (uint32_t)P);
     float acc[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) acc[k] = (bias && k < K) ? bias[k] : 0.f;
-    for (int sx = (ox + pad) % stride; sx < S; sx += stride) {
-      const int d = ox + pad - sx;
-      if (d < 0) break;                             // larger sx only moves further left
-      const int ix = d / stride;
-      if (ix >= W) continue;
-      for (int j = 0; j < nry; ++j) {
-        const __nv_bfloat16* t = T + (((int64_t)n * H + iyv[j]) * W + ix) * t_pitch + ry[j] * S + sx;
+    for (int r = (oy + pad) % stride; r < R; r += stride) {
+      const int dy = oy + pad - r;
+      if (dy < 0) break;                            // larger r only moves further up
+      const int iy = dy / stride;
+      if (iy >= H) continue;
+      for (int sx = (ox + pad) % stride; sx < S; sx += stride) {
+        const int dx = ox + pad - sx;
+        if (dx < 0) break;
+        const int ix = dx / stride;
+        if (ix >= W) continue;
+        const __nv_bfloat16* t = T + (((int64_t)n * H + iy) * W + ix) * t_pitch + r * S + sx;
 #pragma unroll
         for (int k = 0; k < KMAX; ++k)
           if (k < K) acc[k] += __bfloat162float(t[k * TP]);
       }
     }
-    const int64_t o = (int64_t)row * Q + ox;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
-      if (k < K) icf::st_any(out, out_dtype, o * out_pitch + k, icf::apply_act(acc[k], act, slope));
+      if (k < K) icf::st_any(out, out_dtype, (int64_t)o * out_pitch + k, icf::apply_act(acc[k], act, slope));
   }
 }
 
@@ -293,18 +293,18 @@ int icf_col2im_taps(const void* T, int32_t t_pitch, int32_t TP, int32_t N, int32
                   TP >= R * S && t_pitch >= K * TP && out_pitch >= K,
               "icf_col2im_taps: bad arguments");
   if (N == 0) return 0;
-  ICF_REQUIRE(K <= 8 && (R + stride - 1) / stride <= 4 && (int64_t)N * P < 0x7fffffffLL, "icf_col2im_taps: at most 8 channels, 4 rows per parity");
-  const dim3 grid((unsigned)(N * P), (unsigned)((Q + LT - 1) / LT));
+  ICF_REQUIRE(K <= 8 && (int64_t)N * P < 0x7fffffffLL, "icf_col2im_taps: at most 8 channels");
+  const int grid = grid_for((int64_t)N * P * Q);
   const __nv_bfloat16* Tb = reinterpret_cast<const __nv_bfloat16*>(T);
   if (K == 1)
-    col2im_taps_kernel<1><<<grid, LT, 0, icf::as_stream(stream)>>>(Tb, t_pitch, TP, H, W, P, Q, K, R, S, stride, pad, bias, act, slope,
-                                                                   out, out_dtype, out_pitch);
+    col2im_taps_kernel<1><<<grid, LT, 0, icf::as_stream(stream)>>>(Tb, t_pitch, TP, N, H, W, P, Q, K, R, S, stride, pad, bias, act,
+                                                                   slope, out, out_dtype, out_pitch);
   else if (K <= 2)
-    col2im_taps_kernel<2><<<grid, LT, 0, icf::as_stream(stream)>>>(Tb, t_pitch, TP, H, W, P, Q, K, R, S, stride, pad, bias, act, slope,
-                                                                   out, out_dtype, out_pitch);
+    col2im_taps_kernel<2><<<grid, LT, 0, icf::as_stream(stream)>>>(Tb, t_pitch, TP, N, H, W, P, Q, K, R, S, stride, pad, bias, act,
+                                                                   slope, out, out_dtype, out_pitch);
   else
-    col2im_taps_kernel<8><<<grid, LT, 0, icf::as_stream(stream)>>>(Tb, t_pitch, TP, H, W, P, Q, K, R, S, stride, pad, bias, act, slope,
-                                                                   out, out_dtype, out_pitch);
+    col2im_taps_kernel<8><<<grid, LT, 0, icf::as_stream(stream)>>>(Tb, t_pitch, TP, N, H, W, P, Q, K, R, S, stride, pad, bias, act,
+                                                                   slope, out, out_dtype, out_pitch);
   return icf::check_launch("col2im_taps");
 }
 

@@ -268,3 +268,26 @@ def test_reference_written_pickle_runs_on_the_engine():
         cf = G2(E2(images.to(DEV), to_dev(c)), to_dev(c_cf))
     ref = R.counterfactual(fam, sdE, sdG, images, c, c_cf)
     assert rel_err(cf, ref) < 1e-3
+
+
+def test_load_model_state_dict_checkpoint(tmp_path):
+    """mnist.load_model (mnist.py:302-313): a checkpoint of reference-layout state dicts round-trips through the drop-in classes,
+    and state dicts exported by them load into nothing else than the same keys / shapes (App. A.5 of the survey)."""
+    m = family_module("mnist")
+    fam, n, seed = "mnist", 4, 33
+    sds = {k: R.synth_state_dict(fam, k, seed, 0.05) for k in "EGD"}
+    path = str(tmp_path / "ck.tar")
+    torch.save({"E_state_dict": sds["E"], "G_state_dict": sds["G"], "D_state_dict": sds["D"], "epoch": 3}, path)
+    E, G, D, raw = m.load_model(path, device=DEV, return_raw=True)
+    assert raw["epoch"] == 3 and isinstance(E, m.Encoder) and isinstance(D, m.Discriminator)
+    for net, k in ((E, "E"), (G, "G"), (D, "D")):
+        got = net.state_dict()
+        assert list(got.keys()) == list(sds[k].keys())
+        assert all(torch.equal(got[key].cpu(), sds[k][key]) for key in got)
+    images, c, z, c_cf = golden_inputs(fam, n, seed)
+    E.to(DEV), G.to(DEV)
+    with torch.no_grad():
+        cf = G(E(images.to(DEV), to_dev(c)), to_dev(c_cf))
+    assert rel_err(cf, R.counterfactual(fam, sds["E"], sds["G"], images, c, c_cf)) < 1e-3
+    planes = m.continuous_feature_map(torch.tensor([[0.5], [-1.0]]), (28, 28))
+    assert planes.shape == (2, 1, 28, 28) and float(planes[1].max()) == -1.0
