@@ -280,3 +280,73 @@ def test_bce_adam_cast_fill():
     ops.fill_f32(a.data_ptr(), 2.5, 1000)
     torch.cuda.synchronize()
     assert float(a.min()) == 2.5 == float(a.max())
+
+
+@pytest.mark.parametrize("case", [(3, 16, 9, 1, 5, 2, 2, 1), (2, 24, 7, 2, 5, 2, 1, 0), (2, 8, 6, 1, 3, 2, 1, 0), (130, 64, 5, 1, 5, 2, 2, 1)],
+                         ids=str)
+def test_taps_as_channels_transposed_conv(case):
+    """icf_conv_forward (plain GEMM over the input pixels, taps as output columns) + icf_col2im_taps == conv_transpose2d for
+    stride-2 layers with 1-2 output channels (audio_mnist.py:242 ConvTranspose2d(64, 1, 5, 2, 2, 1)), and icf_im2col_taps +
+    GEMM == its data gradient (conv2d of the one-channel gradient)."""
+    ops = ops_mod()
+    n, C, H, K, k, s, p, op = case
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(n, C, H, H, generator=g)
+    w = 0.2 * torch.randn(C, K, k, k, generator=g)                     # ConvTranspose2d layout [Cin][Cout][R][S]
+    b = torch.randn(K, generator=g)
+    P = (H - 1) * s - 2 * p + k + op
+    T_, TP = k * k, (k * k + 7) // 8 * 8 if K == 1 else k * k
+    cols = K * TP if K == 1 else (K * T_ + 7) // 8 * 8
+    xb = x.bfloat16().float()
+    wb = w.bfloat16().float()
+    # operand rows (k, tap) x channels:  rows[kk*TP + t][c] = w[c][kk][t]
+    wrows = torch.zeros(cols, C)
+    for kk in range(K):
+        wrows[kk * TP:kk * TP + T_] = wb[:, kk].reshape(C, T_).t()
+    wd = wrows.bfloat16().to(DEV).contiguous()
+    xd = nhwc(xb, C, torch.bfloat16)
+    Tm = torch.empty(n * H * H, cols, dtype=torch.bfloat16, device=DEV)
+    ops.conv_forward(1, ops.GATHER, n, H, H, C, C, H, H, K * TP if K == 1 else K * T_, cols, 1, 1, 1, 0, xd.data_ptr(), wd.data_ptr(),
+                     cols, C, Tm.data_ptr())
+    out = torch.empty(n * P * P, 8, dtype=torch.float32, device=DEV)
+    b_d = b.to(DEV)
+    ops.col2im_taps(Tm.data_ptr(), cols, TP, n, H, H, P, P, K, k, k, s, p, b_d.data_ptr(), "tanh", 0.0, out.data_ptr(), 0, 8)
+    ref = torch.tanh(F.conv_transpose2d(xb.double(), wb.double(), b.double(), stride=s, padding=p, output_padding=op))
+    got = from_nhwc(out, n, P, P, K)
+    assert rel_err(got, ref) < 2e-2
+    if K == 1:
+        # data gradient of the one-output-channel layer: dX[c] = conv2d(dOut, w[c]) = im2col(dOut) [pixels, taps] x w[taps, c]
+        dy = torch.randn(n, 1, P, P, generator=g)
+        dyd = nhwc(dy.bfloat16().float(), 8, torch.bfloat16)
+        A = torch.empty(n * H * H, TP, dtype=torch.bfloat16, device=DEV)
+        ops.im2col_taps(dyd.data_ptr(), 1, 8, n, P, P, H, H, k, k, s, p, A.data_ptr(), TP)
+        wt = torch.zeros(C, TP)
+        wt[:, :T_] = wb[:, 0].reshape(C, T_)
+        dx = torch.empty(n * H * H, C, dtype=torch.bfloat16, device=DEV)
+        wt_d = wt.bfloat16().to(DEV)
+        ops.conv_forward(1, ops.GATHER, n, H, H, T_, TP, H, H, C, C, 1, 1, 1, 0, A.data_ptr(), wt_d.data_ptr(), C, TP, dx.data_ptr())
+        ref_dx = F.conv2d(dy.bfloat16().double(), wb.double()[:, :1], stride=s, padding=p)
+        # conv2d with weight [C][1][k][k] over the one-channel gradient (cross-correlation, as in conv_transpose2d's adjoint)
+        assert rel_err(from_nhwc(dx, n, H, H, C), ref_dx[:, :, :H, :H]) < 2e-2
+
+
+def test_bn_fold_kernels():
+    """icf_bn_fold_weights / icf_bn_fold_wgrad: conv(scale*y + shift; w, b) == conv(y; w', b') and the weight-gradient fix-up."""
+    ops = ops_mod()
+    g = torch.Generator().manual_seed(12)
+    K, T_, C, Cp = 24, 16, 20, 24
+    w = torch.randn(K, T_, Cp, generator=g)
+    w[:, :, C:] = 0
+    scale, shift, bias = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g), torch.randn(K, generator=g)
+    wd, wo, bo = w.to(DEV).contiguous(), torch.empty(K * T_ * Cp, device=DEV), torch.empty(K, device=DEV)
+    sc_d, sh_d, b_d = scale.to(DEV), shift.to(DEV), bias.to(DEV)          # kept alive: raw addresses go to the library
+    ops.bn_fold_weights(wd.data_ptr(), 0, K, T_, Cp, C, sc_d.data_ptr(), sh_d.data_ptr(), b_d.data_ptr(), wo.data_ptr(), bo.data_ptr())
+    ref_w = w.clone()
+    ref_w[:, :, :C] *= scale
+    assert rel_err(wo.reshape(K, T_, Cp), ref_w) < 1e-6
+    assert rel_err(bo, bias + (w[:, :, :C] * shift).sum(dim=(1, 2))) < 1e-5
+    G = torch.randn(K, T_, C, generator=g)
+    db = torch.randn(K, generator=g)
+    Gd, db_d = G.to(DEV).contiguous(), db.to(DEV)
+    ops.bn_fold_wgrad(Gd.data_ptr(), K, T_, C, sc_d.data_ptr(), sh_d.data_ptr(), db_d.data_ptr())
+    assert rel_err(Gd, G * scale + shift * db[:, None, None]) < 1e-6
