@@ -126,6 +126,9 @@ _SIGS = {
     "icf_latent_l2": (_i32, [_vp, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _i32, _vp]),
     "icf_scm_affine_cf": (_i32, [C.POINTER(ScmAffineArgs), _vp]),
     "icf_onehot_swap": (_i32, [_vp, _i32, _vp, _i64, _i32, _vp, _vp]),
+    "icf_log_spectrogram": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp]),
+    "icf_spect_stats": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
+    "icf_spect_to_img": (_i32, [_vp, _vp, _vp, _i64, _i32, _f32, _vp, _i32, _vp]),
     "icf_col2im_taps": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _f32, _vp,
                                 _i32, _i32, _vp]),
     "icf_im2col_taps": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),

@@ -228,6 +228,23 @@ int icf_scale_shift_mask(const void* y, int32_t y_dtype, int32_t y_pitch, void* 
                          int32_t u_pitch, int64_t pixels, int32_t pixels_per_sample, int32_t C,
                          const float* scale, const float* shift, const float* mask, int32_t mask_pitch,
                          void* stream);
+/* ------------------------------------------------------------------------------------------------
+ * Spectrogram front end, the step in front of the hot path for the spectrogram families:
+ *   icf_log_spectrogram  = torchaudio.transforms.Spectrogram(n_fft, win_length, pad) followed by (. + eps).log()
+ *                          (audio_mnist.py:59-61,116: n_fft 255, win_length 128, pad 96, hop = win_length/2, eps 1e-6):
+ *                          zero padding by `pad`, reflect centring by n_fft/2, periodic Hann window of win_length centred in
+ *                          the n_fft frame, one-sided power spectrum.  wave fp32 [N][L] -> out fp32 [N][n_fft/2+1][frames],
+ *                          frames = 1 + (L + 2*pad + 2*(n_fft/2) - n_fft)/hop.
+ *   icf_spect_stats      sum[t] += sum_rows s[row][t], sumsq[t] += sum_rows s^2   (audio_mnist.py:347-358: statistics per time
+ *                          frame over clips and frequency bins; the caller divides by the row count)
+ *   icf_spect_to_img     clip((s - mean[t])/(std[t] + 1e-6), -k, k)/k             (audio_mnist.py:361-363), out f32 or bf16
+ * ------------------------------------------------------------------------------------------------ */
+int icf_log_spectrogram(const float* wave, int64_t N, int32_t L, int32_t n_fft, int32_t win_length, int32_t hop, int32_t pad,
+                        float eps, float* out, int32_t frames, void* stream);
+int icf_spect_stats(const float* s, int64_t rows, int32_t T, float* sum, float* sumsq, void* stream);
+int icf_spect_to_img(const float* s, const float* mean, const float* std_, int64_t rows, int32_t T, float stds_kept, void* out,
+                     int32_t out_dtype, void* stream);
+
 /* "Taps as channels" for the layers with ONE (or very few) channels on one side and a stride-2 5x5 filter — the generator tail
  * ConvTranspose2d(C, 1, 5, 2, 2, 1) (audio_mnist.py:242, whalecalls.py:306, esrf_acoustic.py:197) and the data gradient of the
  * first conv towards the attribute-plane channels: the contraction over the C channels runs as a plain 1x1 icf_conv_forward /

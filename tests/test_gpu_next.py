@@ -239,3 +239,35 @@ def test_explainer_style_search_through_generator():
         assert abs(a - b) <= 1e-3 * max(abs(b), 0.1), (got, want)
     for k in p_ref:
         assert rel_err(p_got[k], p_ref[k]) < 2e-3, k
+
+
+def test_spectrogram_front_end_vs_oracle():
+    """Row N4: waveform -> log-power spectrogram (audio_mnist.py:59-61,116) -> per-frame statistics (:347-358) -> spect_to_img
+    (:361-363) on the device against the float64 restatement of torchaudio's transform."""
+    from icf_b200.spectro import LogSpectrogram, SpectrogramNormalizer
+    from oracle import spectro_ref
+    g = torch.Generator().manual_seed(8)
+    waves = [0.3 * torch.randn(5, 8000, generator=g) * (1 + torch.arange(8000) / 4000.0), 0.1 * torch.randn(3, 8000, generator=g)]
+    waves[1][:, 4000:] = 0.0                                   # trailing silence: zero-padded clips as in the dataset (:84-92)
+    front = LogSpectrogram()
+    specs = [front(w.to(DEV)) for w in waves]
+    refs = [spectro_ref.log_spectrogram(w) for w in waves]
+    for s, r in zip(specs, refs):
+        assert s.shape == r.shape == (r.shape[0], 128, 128)
+        # log(power + 1e-6): bins whose power is at the 1e-6 floor amplify fp32 rounding of the DFT sum; the bound is absolute in the log
+        assert float((s.cpu().double() - r).abs().max()) < 5e-3
+        assert rel_err(s, r) < 1e-4
+    norm = SpectrogramNormalizer(128, torch.device(DEV))
+    for s in specs:
+        norm.update(s)
+    mean, std = norm.finalize()
+    rm, rs = spectro_ref.frame_stats(refs)
+    assert rel_err(mean, rm) < 1e-4 and rel_err(std, rs) < 1e-3
+    for s, r in zip(specs, refs):
+        img = norm.to_img(s)
+        want = spectro_ref.spect_to_img(r, rm, rs)
+        assert float((img.cpu().double() - want).abs().max()) < 2e-3 and float(img.abs().max()) <= 1.0
+        assert norm.to_img(s, dtype=torch.bfloat16).dtype == torch.bfloat16
+        back = norm.to_spect(img)
+        inside = (want.abs() < 0.999).to(DEV)                    # un-clipped entries invert exactly
+        assert float((back - s)[inside].abs().max()) < 5e-3

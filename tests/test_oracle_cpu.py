@@ -151,3 +151,15 @@ def test_scm_hyper_network_form_is_invertible():
     ok = s.abs() < 10          # beyond that the sigmoid saturates and SigmoidTransform's clamp (1 - eps) discards the noise
     assert int(ok.sum()) > 150
     assert torch.allclose(e_hat[ok], eps[ok], atol=1e-4) and torch.allclose(v_same, inten, atol=1e-4)
+
+
+def test_log_spectrogram_oracle_matches_torchaudio():
+    """oracle/spectro_ref.py against the reference's own call, torchaudio.transforms.Spectrogram(n_fft=255, win_length=128, pad=96)
+    (audio_mnist.py:59-61) + (. + 1e-6).log() (:116)."""
+    torchaudio = pytest.importorskip("torchaudio")
+    from oracle import spectro_ref
+    g = torch.Generator().manual_seed(6)
+    wave = torch.randn(3, 8000, generator=g)
+    ref = (torchaudio.transforms.Spectrogram(n_fft=255, win_length=128, pad=96)(wave) + 1e-6).log()
+    got = spectro_ref.log_spectrogram(wave)
+    assert got.shape == (3, 128, 128) and torch.allclose(got.float(), ref, atol=2e-4, rtol=1e-4)
