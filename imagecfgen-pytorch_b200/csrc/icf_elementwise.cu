@@ -44,89 +44,96 @@ __global__ void argmax_rows_kernel(const void* x, int dt, int n, int k, int32_t*
 // stream the pixels: one 4-byte read of the image and one 16-byte store of the (<= 8 channel) vector per pixel.
 // grid = (samples, pixel slabs): big images (512x512) are split so that a small batch still fills the machine.
 // ------------------------------------------------------------------------------------------------
+constexpr int IMGFEAT_MAX_W = 1024;
 __global__ void __launch_bounds__(EW_THREADS) imgfeat_fwd_kernel(const icf_imgfeat_args a) {
   __shared__ float plane[ICF_MAX_PLANES - 1][256];
-  __shared__ float cst[8], mk0;
-  __shared__ uint8_t cxs[640];                                          // cell column of every padded x (W + 2 pad <= 640)
+  __shared__ float cst[8], mk0_s;
+  __shared__ uint8_t cxs[IMGFEAT_MAX_W], cys[IMGFEAT_MAX_W];           // cell column / row of every padded x / y (255 = border)
   const int Hp = a.H + 2 * a.pad, Wp = a.W + 2 * a.pad;
   const int rows_per = (Hp + (int)gridDim.y - 1) / (int)gridDim.y;
   const int y_lo = (int)blockIdx.y * rows_per, y_hi = min(Hp, y_lo + rows_per);
   const bool vec = a.dtype == ICF_BF16 && a.feat_pitch == 8;           // one 16-byte store per pixel
+  const bool xf32 = a.x_dtype == ICF_F32;
   const int n_emb = a.n_emb < ICF_MAX_PLANES - 1 ? a.n_emb : ICF_MAX_PLANES - 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int xp = threadIdx.x; xp < Wp; xp += EW_THREADS) {
+  const int NT = (int)blockDim.x, NW = NT >> 5;                        // 64 threads for small images, 256 for large ones
+  for (int xp = threadIdx.x; xp < Wp; xp += NT) {
     const int x = xp - a.pad;
     cxs[xp] = (uint8_t)((x >= 0 && x < a.W) ? min((x * 16) / a.W, 15) : 255);   // nearest: floor(dst*16/size); 255 = border
   }
+  for (int yp = threadIdx.x; yp < Hp; yp += NT) {
+    const int y = yp - a.pad;
+    cys[yp] = (uint8_t)((y >= 0 && y < a.H) ? min((y * 16) / a.H, 15) : 255);
+  }
   for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
     const float* mk = a.mask ? a.mask + (int64_t)n * a.mask_pitch : nullptr;
-    for (int t = threadIdx.x; t < n_emb * 256; t += EW_THREADS) {
+    for (int t = threadIdx.x; t < n_emb * 256; t += NT) {
       const int e = t >> 8, cell = t & 255;
       const float v = tanhf(a.emb_table[e][(int64_t)a.emb_index[e][n] * 256 + cell]);
       plane[e][cell] = (mk && 1 + e < 8) ? v * mk[1 + e] : v;
     }
-    if ((int)threadIdx.x < a.n_cont && 1 + n_emb + (int)threadIdx.x < 8) {
-      const int ch = 1 + n_emb + (int)threadIdx.x;
-      const float v = a.cont[threadIdx.x][n];
-      cst[threadIdx.x] = mk ? v * mk[ch] : v;
+    if (threadIdx.x < 8) {                                             // cst[channel]: constant planes, 0 elsewhere
+      const int e = (int)threadIdx.x - 1 - n_emb;
+      float v = 0.f;
+      if (e >= 0 && e < a.n_cont) { v = a.cont[e][n]; if (mk) v *= mk[threadIdx.x]; }
+      cst[threadIdx.x] = v;
     }
-    if (threadIdx.x == 0) mk0 = mk ? mk[0] : 1.f;
+    if (threadIdx.x == 0) mk0_s = mk ? mk[0] : 1.f;
     __syncthreads();
-    // One warp per (padded) image row, 32 pixels per pass: no per-pixel division.  The kernel is bound by the latency of the image
-    // loads (ncu: the consumer of the load holds 22 % of the stall samples, one 128-byte request in flight per warp), so a warp
-    // first issues the loads of up to four (row, 32-pixel chunk) items, then does the math and the stores.
-    const int xchunks = (Wp + 31) >> 5;
-    const int items = (y_hi - y_lo) * xchunks;
-    constexpr int NW = EW_THREADS / 32, UN = 4;
-    for (int it0 = warp; it0 < items; it0 += NW * UN) {
-      float xv[UN];
-      int cellv[UN];
+    // One warp per (padded) image row, 32 pixels per pass.  The first version of this loop was INSTRUCTION bound (ncu: 52 % SM
+    // busy at 2 % of DRAM, ~220 instructions per pixel): two integer divisions per pixel and pass, 64-bit index arithmetic and a
+    // run-time dtype switch per access.  Now the nearest-neighbour cell of a row / column comes from the two tables above, the
+    // row base pointers are computed once per row, and the loads of UN rows are issued before their math and stores.
+    const float mk0 = mk0_s;
+    constexpr int UN = 4;
+    const int64_t x_img = (int64_t)n * a.H * a.W;
+    const int64_t o_img = (int64_t)n * Hp * Wp;
+    for (int r0 = y_lo + warp; r0 < y_hi; r0 += NW * UN) {
+      for (int xp = lane; xp < Wp; xp += 32) {
+        const int cx = cxs[xp];
+        float xv[UN];
+        int cellv[UN];
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int it = it0 + u * NW;
-        xv[u] = 0.f;
-        cellv[u] = -1;
-        if (it < items) {
-          const int yr = it / xchunks, xp = (it - yr * xchunks) * 32 + lane, yp = y_lo + yr;
-          const int y = yp - a.pad;
-          if (xp < Wp && y >= 0 && y < a.H) {
-            const int cx = cxs[xp];
-            if (cx != 255) {
-              cellv[u] = min((y * 16) / a.H, 15) * 16 + cx;
-              xv[u] = icf::ld_any(a.x, a.x_dtype, (((int64_t)n * a.H + y) * a.W + (xp - a.pad)) * a.x_pitch);
+        for (int u = 0; u < UN; ++u) {
+          const int yp = r0 + u * NW;
+          xv[u] = 0.f;
+          cellv[u] = -1;
+          if (yp < y_hi) {
+            const int cy = cys[yp];
+            if (cy != 255 && cx != 255) {
+              cellv[u] = cy * 16 + cx;
+              const int64_t xi = (x_img + (int64_t)(yp - a.pad) * a.W + (xp - a.pad)) * a.x_pitch;
+              xv[u] = xf32 ? reinterpret_cast<const float*>(a.x)[xi]
+                           : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.x)[xi]);
             }
           }
         }
-      }
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int it = it0 + u * NW;
-        if (it >= items) continue;
-        const int yr = it / xchunks, xp = (it - yr * xchunks) * 32 + lane, yp = y_lo + yr;
-        if (xp >= Wp) continue;
-        float f[8];
+        for (int u = 0; u < UN; ++u) {
+          const int yp = r0 + u * NW;
+          if (yp >= y_hi) continue;
+          float f[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = 0.f;
-        if (cellv[u] >= 0) {
-          f[0] = xv[u] * mk0;
-          int ch = 1;
+          for (int j = 0; j < 8; ++j) f[j] = 0.f;
+          if (cellv[u] >= 0) {
+            f[0] = xv[u] * mk0;
 #pragma unroll
-          for (int e = 0; e < ICF_MAX_PLANES - 1; ++e)
-            if (e < n_emb) { f[ch] = plane[e][cellv[u]]; ++ch; }
-#pragma unroll
-          for (int e = 0; e < ICF_MAX_PLANES - 1; ++e)
-            if (e < a.n_cont && ch < 8) { f[ch] = cst[e]; ++ch; }
-        }
-        const int64_t o = ((int64_t)n * Hp + yp) * Wp + xp;
-        if (vec) {
-          uint4 w;
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
-          __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
-          w.x = *reinterpret_cast<uint32_t*>(&p0); w.y = *reinterpret_cast<uint32_t*>(&p1);
-          w.z = *reinterpret_cast<uint32_t*>(&p2); w.w = *reinterpret_cast<uint32_t*>(&p3);
-          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.feat) + o * 8) = w;
-        } else {
-          for (int ch = 0; ch < a.feat_pitch; ++ch) icf::st_any(a.feat, a.dtype, o * a.feat_pitch + ch, ch < 8 ? f[ch] : 0.f);
+            for (int j = 1; j < 8; ++j) {                               // embedded planes first, then the constant planes
+              const int e = j - 1;
+              f[j] = e < n_emb ? plane[e][cellv[u]] : cst[j];
+            }
+          }
+          const int64_t o = o_img + (int64_t)yp * Wp + xp;
+          if (vec) {
+            uint4 w;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
+            w.x = *reinterpret_cast<uint32_t*>(&p0); w.y = *reinterpret_cast<uint32_t*>(&p1);
+            w.z = *reinterpret_cast<uint32_t*>(&p2); w.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.feat) + o * 8) = w;
+          } else {
+            for (int ch = 0; ch < a.feat_pitch; ++ch) icf::st_any(a.feat, a.dtype, o * a.feat_pitch + ch, ch < 8 ? f[ch] : 0.f);
+          }
         }
       }
     }
@@ -1118,10 +1125,15 @@ int icf_image_features_fwd(const icf_imgfeat_args* a, void* stream) {
   if (total == 0) return 0;
   const int sms = icf::sm_count();
   const int Hp = a->H + 2 * a->pad, Wp = a->W + 2 * a->pad;
-  ICF_REQUIRE(Wp <= 640 && Hp <= 65535, "icf_image_features_fwd: images wider than 640 (padded) are not supported");
-  int gx = a->N < sms * 8 ? a->N : sms * 8, gy = 1;
+  ICF_REQUIRE(Wp <= IMGFEAT_MAX_W && Hp <= IMGFEAT_MAX_W, "icf_image_features_fwd: images larger than 1024 (padded) are not supported");
+  // The per-sample chain (index load -> table load -> tanh -> barrier -> image loads -> stores) is latency, not bandwidth: with
+  // 256-thread blocks three resident blocks per SM each walked ~9 samples of 28x28 pixels one after the other (51 us for 67 MB).
+  // Small images get 64-thread blocks, 12+ of them per SM, so that many samples are in flight on every SM.
+  const int threads = (int64_t)Hp * Wp <= 4096 ? 64 : EW_THREADS;
+  const int per_sm = threads == 64 ? 16 : 8;
+  int gx = a->N < sms * per_sm ? a->N : sms * per_sm, gy = 1;
   while (gx * gy < 2 * sms && Hp / (gy * 2) >= 8 && gy < 64) gy *= 2;            // few, large images: split the rows
-  imgfeat_fwd_kernel<<<dim3((unsigned)gx, (unsigned)gy), EW_THREADS, 0, icf::as_stream(stream)>>>(*a);
+  imgfeat_fwd_kernel<<<dim3((unsigned)gx, (unsigned)gy), threads, 0, icf::as_stream(stream)>>>(*a);
   return icf::check_launch("imgfeat_fwd");
 }
 

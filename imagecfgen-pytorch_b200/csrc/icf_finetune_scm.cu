@@ -249,6 +249,83 @@ inline int grid_for(int64_t total) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Gradient-based counterfactual explainer (explain/cf_example.py:130-160): the optimised variables are raw rows; the generator
+// sees tanh(raw) (latent code, continuous attributes) or softmax(raw) (categorical attributes).  One warp per (group, row).
+// ------------------------------------------------------------------------------------------------
+struct ExplainGroups { icf_explain_group g[ICF_EXPLAIN_MAX_GROUPS]; int n; };
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void explain_transform_kernel(const float* __restrict__ raw, float* __restrict__ out, ExplainGroups gs, int64_t rows) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= rows * gs.n) return;
+  const int gi = (int)(w / rows);
+  const int64_t r = w - (int64_t)gi * rows;
+  const icf_explain_group g = gs.g[gi];
+  const float* x = raw + g.offset + r * g.width;
+  float* y = out + g.offset + r * g.width;
+  if (g.mode == ICF_EXPLAIN_SOFTMAX) {
+    float mx = -INFINITY;
+    for (int j = lane; j < g.width; j += 32) mx = fmaxf(mx, x[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < g.width; j += 32) sum += expf(x[j] - mx);
+    sum = warp_sum(sum);
+    for (int j = lane; j < g.width; j += 32) y[j] = expf(x[j] - mx) / sum;
+  } else if (g.mode == ICF_EXPLAIN_TANH) {
+    for (int j = lane; j < g.width; j += 32) y[j] = tanhf(x[j]);
+  } else {
+    for (int j = lane; j < g.width; j += 32) y[j] = x[j];
+  }
+}
+
+// draw = dout * d(out)/d(raw) through the saved outputs: tanh' = 1 - y^2;  softmax: y * (g - sum_j g_j y_j)
+__global__ void explain_backward_kernel(const float* __restrict__ out, float* __restrict__ draw, ExplainGroups gs, int64_t rows) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= rows * gs.n) return;
+  const int gi = (int)(w / rows);
+  const int64_t r = w - (int64_t)gi * rows;
+  const icf_explain_group g = gs.g[gi];
+  const float* y = out + g.offset + r * g.width;
+  float* dx = draw + g.offset + r * g.width;
+  const float* dy = g.dout ? g.dout + r * g.width : nullptr;
+  if (!dy) {
+    for (int j = lane; j < g.width; j += 32) dx[j] = 0.f;
+  } else if (g.mode == ICF_EXPLAIN_SOFTMAX) {
+    float dot = 0.f;
+    for (int j = lane; j < g.width; j += 32) dot = fmaf(dy[j], y[j], dot);
+    dot = warp_sum(dot);
+    for (int j = lane; j < g.width; j += 32) dx[j] = y[j] * (dy[j] - dot);
+  } else if (g.mode == ICF_EXPLAIN_TANH) {
+    for (int j = lane; j < g.width; j += 32) dx[j] = dy[j] * (1.f - y[j] * y[j]);
+  } else {
+    for (int j = lane; j < g.width; j += 32) dx[j] = dy[j];
+  }
+}
+
+static int explain_groups(const icf_explain_group* groups, int32_t n_groups, ExplainGroups* gs) {
+  if (!groups || n_groups < 0 || n_groups > ICF_EXPLAIN_MAX_GROUPS) return 1;
+  gs->n = n_groups;
+  for (int i = 0; i < n_groups; ++i) {
+    if (groups[i].width <= 0 || groups[i].offset < 0) return 1;
+    gs->g[i] = groups[i];
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -339,6 +416,27 @@ int icf_onehot_swap(const void* idx, int32_t idx_is_int64, const uint8_t* mask, 
   if (n == 0) return 0;
   onehot_swap_kernel<<<grid_for(n * K), LT, 0, icf::as_stream(stream)>>>(idx, idx_is_int64, mask, n, K, rows);
   return icf::check_launch("onehot_swap");
+}
+
+
+int icf_explain_transform(const float* raw, float* out, const icf_explain_group* groups, int32_t n_groups, int64_t rows,
+                          void* stream) {
+  ExplainGroups gs;
+  ICF_REQUIRE(raw && out && rows >= 0 && explain_groups(groups, n_groups, &gs) == 0, "icf_explain_transform: bad arguments");
+  if (rows == 0 || n_groups == 0) return 0;
+  const int64_t threads = rows * n_groups * 32;
+  explain_transform_kernel<<<(unsigned)icf::cdiv(threads, (int64_t)128), 128, 0, icf::as_stream(stream)>>>(raw, out, gs, rows);
+  return icf::check_launch("explain_transform");
+}
+
+int icf_explain_backward(const float* out, float* draw, const icf_explain_group* groups, int32_t n_groups, int64_t rows,
+                         void* stream) {
+  ExplainGroups gs;
+  ICF_REQUIRE(out && draw && rows >= 0 && explain_groups(groups, n_groups, &gs) == 0, "icf_explain_backward: bad arguments");
+  if (rows == 0 || n_groups == 0) return 0;
+  const int64_t threads = rows * n_groups * 32;
+  explain_backward_kernel<<<(unsigned)icf::cdiv(threads, (int64_t)128), 128, 0, icf::as_stream(stream)>>>(out, draw, gs, rows);
+  return icf::check_launch("explain_backward");
 }
 
 }  // extern "C"

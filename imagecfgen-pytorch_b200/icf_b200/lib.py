@@ -90,6 +90,10 @@ class ScmAffineArgs(C.Structure):
                 ("parent_cf_out", _vp), ("value_cf_scaled", _vp), ("parent_cf_scaled", _vp)]
 
 
+class ExplainGroup(C.Structure):
+    _fields_ = [("mode", _i32), ("width", _i32), ("offset", _i64), ("dout", _vp)]
+
+
 _SIGS = {
     "icf_last_error": (C.c_char_p, []),
     "icf_version": (_i32, []),
@@ -126,6 +130,8 @@ _SIGS = {
     "icf_latent_l2": (_i32, [_vp, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _i32, _vp]),
     "icf_scm_affine_cf": (_i32, [C.POINTER(ScmAffineArgs), _vp]),
     "icf_onehot_swap": (_i32, [_vp, _i32, _vp, _i64, _i32, _vp, _vp]),
+    "icf_explain_transform": (_i32, [_vp, _vp, C.POINTER(ExplainGroup), _i32, _i64, _vp]),
+    "icf_explain_backward": (_i32, [_vp, _vp, C.POINTER(ExplainGroup), _i32, _i64, _vp]),
     "icf_log_spectrogram": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp]),
     "icf_spect_stats": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "icf_spect_to_img": (_i32, [_vp, _vp, _vp, _i64, _i32, _f32, _vp, _i32, _vp]),

@@ -293,6 +293,22 @@ def latent_l2(z, z_dtype, z_pitch, n, latent, weight, loss_out, dz, accumulate):
             1 if accumulate else 0)
 
 
+def explain_groups(specs):
+    """specs: [(mode, width, offset, dout_ptr | None)] -> ctypes array for icf_explain_transform / icf_explain_backward."""
+    arr = (_l.ExplainGroup * len(specs))()
+    for g, (mode, width, offset, dout) in zip(arr, specs):
+        g.mode, g.width, g.offset, g.dout = mode, width, offset, dout
+    return arr
+
+
+def explain_transform(raw, out, groups, rows):
+    _launch("icf_explain_transform", _l.load().icf_explain_transform, raw, out, groups, len(groups), rows)
+
+
+def explain_backward(out, draw, groups, rows):
+    _launch("icf_explain_backward", _l.load().icf_explain_backward, out, draw, groups, len(groups), rows)
+
+
 def scm_affine_cf(args):
     _launch("icf_scm_affine_cf", _l.load().icf_scm_affine_cf, C.byref(args))
 

@@ -57,7 +57,10 @@ class SpectrogramNormalizer:
 
     def finalize(self):
         self.mean = self.mean_sum / self.batches                      # E[X]
-        self.std = torch.sqrt(self.sq_sum / self.batches - self.mean.square())
+        # E[X^2] - E[X]^2 as upstream (:356-357), clamped at 0: a frame that is constant over the whole dataset (the zero-padded
+        # first frame is log(eps) everywhere) leaves a difference of rounding size and either sign; upstream's sqrt returns NaN
+        # for the negative ones and poisons every image of spect_to_img — here such a frame gets std 0 (-> divided by 1e-6).
+        self.std = torch.sqrt((self.sq_sum / self.batches - self.mean.square()).clamp_min_(0.0))
         return self.mean, self.std
 
     def to_img(self, s: torch.Tensor, dtype=torch.float32) -> torch.Tensor:

@@ -379,6 +379,30 @@ int icf_onehot_swap(const void* idx, int32_t idx_is_int64, const uint8_t* mask, 
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Gradient-based counterfactual explainer (explain/cf_example.py:80-170 HingeLossCFExplainer.explain): per image the
+ * optimised variables are RAW rows — one per attribute that is not ignored (:121-125) and, with train_z, the latent code
+ * (:129-130); the generator is fed softmax(raw) for categorical attributes, tanh(raw) for the others and for z (:139-147).
+ * All raw rows of a batch of images live in ONE flat fp32 buffer (group g = a [rows][width] block at `offset`), so that
+ * the forward map, its backward and torch.optim.Adam (icf_adam_step over the flat buffer) are three launches per step.
+ *   icf_explain_transform: out[g] = f_g(raw[g])
+ *   icf_explain_backward : draw[g] = dout_g * f_g'(raw[g]) from the saved outputs (dout NULL -> 0)
+ * ------------------------------------------------------------------------------------------------ */
+#define ICF_EXPLAIN_MAX_GROUPS 12
+#define ICF_EXPLAIN_COPY 0
+#define ICF_EXPLAIN_TANH 1
+#define ICF_EXPLAIN_SOFTMAX 2
+typedef struct icf_explain_group {
+  int32_t mode;                  /* ICF_EXPLAIN_* */
+  int32_t width;                 /* elements per row */
+  int64_t offset;                /* of the group's [rows][width] block in the flat buffers (elements) */
+  const float* dout;             /* backward: gradient w.r.t. the transformed rows, [rows][width] fp32, or NULL */
+} icf_explain_group;
+int icf_explain_transform(const float* raw, float* out, const icf_explain_group* groups /* host */, int32_t n_groups,
+                          int64_t rows, void* stream);
+int icf_explain_backward(const float* out, float* draw, const icf_explain_group* groups /* host */, int32_t n_groups,
+                         int64_t rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * torch.optim.Adam (mnist.py:176-179; eps 1e-8, no weight decay) over one flat fp32 buffer.
  * `state` = {step, lr, beta1, beta2, eps, grad_scale} in device memory so a captured CUDA graph can
  * be replayed: the kernel itself advances `step`.

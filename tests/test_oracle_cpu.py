@@ -14,7 +14,7 @@ from oracle import np_ops
 from helpers import golden_inputs, rel_err, digest_close
 
 torch.set_num_threads(max(1, os.cpu_count() or 1))
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")) if not os.path.basename(p).startswith("explain_"))
 # ESRF (723 M parameters): its forward is replayed in the default CPU suite; gradients and the train step of that family
 # (~15 GB of host memory, about a minute) only with ICF_HEAVY=1 — loss, Adam and loop body are family-independent and
 # pinned by the other three families
@@ -163,3 +163,46 @@ def test_log_spectrogram_oracle_matches_torchaudio():
     ref = (torchaudio.transforms.Spectrogram(n_fft=255, win_length=128, pad=96)(wave) + 1e-6).log()
     got = spectro_ref.log_spectrogram(wave)
     assert got.shape == (3, 128, 128) and torch.allclose(got.float(), ref, atol=2e-4, rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# N3: gradient-based explainers — oracle/explain_ref.py against outputs of the reference's own classes
+# (tests/golden/make_golden_explain.py ran /root/reference/explain/cf_example.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def _explain_fixture():
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "explain_mnist_s21.pt"), weights_only=False)
+    sds = {k: R.synth_state_dict("mnist", k, g["seed"], g["std"]) for k in "EG"}
+
+    def clf(img):
+        return img.flatten(1) @ g["clf_w"].t() + g["clf_b"]
+    return g, sds, clf
+
+
+def test_hinge_explainer_oracle_matches_reference():
+    from oracle import explain_ref as X
+    g, sds, clf = _explain_fixture()
+    for h in g["hinge"]:
+        i = h["img"]
+        x = g["x"][i:i + 1]
+        attrs = {k: v[i:i + 1] for k, v in g["c"].items()}
+        trace = []
+        x_cf, _ = X.hinge_explain("mnist", sds["E"], sds["G"], clf, x, attrs, h["init"], target_class=h["target_class"],
+                                  categorical=h["categorical"], ignore=h["ignore"], train_z=h["train_z"], steps=h["steps"],
+                                  lr=h["lr"], trace=trace)
+        assert x_cf.shape == h["x_cf"].shape
+        assert rel_err(x_cf, h["x_cf"]) < 1e-5, (i, rel_err(x_cf, h["x_cf"]))
+        # the optimisation moved the image: the fixture pins a trajectory, not a fixed point
+        assert rel_err(trace[0]["x_cf"], h["x_cf"]) > 1e-3
+
+
+def test_deep_explainer_oracle_matches_reference():
+    from oracle import explain_ref as X
+    g, sds, clf = _explain_fixture()
+    for d in g["deep"]:
+        i = d["img"]
+        x = g["x"][i:i + 1]
+        attrs = {k: v[i:i + 1] for k, v in g["c"].items()}
+        samples, val = X.deep_explain("mnist", sds["E"], sds["G"], clf, x, attrs, "digit", d["target_class"],
+                                      sample_points=d["sample_points"], metric=d["metric"])
+        assert samples.shape == d["samples"].shape and val.shape == d["val"].shape
+        assert rel_err(samples, d["samples"]) < 1e-5 and rel_err(val, d["val"]) < 1e-5

@@ -1,5 +1,10 @@
-CMD="python bench.py --steps 2 --warmup 3 --skip-cf --skip-cpu --skip-torch --no-graph"
-timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 2000 -c 1400 --csv \
-    --log-file gpurun_out/launches_dram_r02.csv $CMD > gpurun_out/ncu_list_dram.log 2>&1
-echo "rc=$?"; tail -2 gpurun_out/ncu_list_dram.log; wc -l gpurun_out/launches_dram_r02.csv
-python -m pytest tests/test_gpu_ops.py -m gpu -q -k "taps or bn_fold" 2>&1 | tail -3
+python -m pytest tests/test_gpu_next.py -m gpu -q -x 2>&1 | tail -30 > gpurun_out/r02_pytest13.log; tail -30 gpurun_out/r02_pytest13.log
+python -m pytest tests/test_gpu_ops.py tests/test_gpu_modules.py -m gpu -q -x -k "feat or forward or mnist" 2>&1 | tail -3
+python bench.py --steps 10 --warmup 3 --skip-cpu --skip-torch --skip-cf > gpurun_out/r02_bench10.json 2> gpurun_out/r02_bench10.err; tail -3 gpurun_out/r02_bench10.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/r02_bench10.json"))
+print({k:d[k] for k in ("value","ms_per_step","launches_per_step","step_tensor_frac")}, d["e2e"]["value"], d["roofline"]["frac"])
+k=d["kernels_ms_per_step"]
+for n,v in list(k.items())[:8]: print(n, v)
+PY
