@@ -17,7 +17,7 @@ OUT = os.path.join(HERE, "icf_b200", "libicf_b200.so")
 STAMP = os.path.join(HERE, "icf_b200", "libicf_b200.srchash")
 OBJ = os.path.join(HERE, "build")
 SOURCES = ["icf_api.cu", "icf_elementwise.cu", "icf_conv_simt.cu", "icf_conv_tc.cu", "icf_conv_ws.cu", "icf_wgrad_px8.cu",
-           "icf_conv_sc.cu", "icf_finetune_scm.cu", "icf_spectro.cu"]
+           "icf_conv_sc.cu", "icf_conv_cm.cu", "icf_finetune_scm.cu", "icf_spectro.cu"]
 
 
 def source_hash() -> str:

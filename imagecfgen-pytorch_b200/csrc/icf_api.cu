@@ -111,6 +111,10 @@ int icf_conv_forward(const icf_conv_args* a, void* stream) {
       int r = icf_sc_conv_forward(a, st);     // scatter-form transposed conv for <= 8 output channels (taps in the MMA N)
       if (r >= 0) { icf::g_conv_path = ICF_PATH_SC; return r; }
     }
+    {
+      int r = icf_cm_conv_forward(a, st);     // unit-stride first layer on 16-byte pixels: accumulator lane = (row, channel)
+      if (r >= 0) { icf::g_conv_path = ICF_PATH_CM; return r; }
+    }
     if (ws_on) {
       int r = icf_ws_conv_forward(a, st);     // weight-stationary row-streaming kernel (small weight slabs)
       if (r >= 0) { icf::g_conv_path = ICF_PATH_WS; return r; }

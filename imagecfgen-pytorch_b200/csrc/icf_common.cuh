@@ -100,5 +100,7 @@ int icf_tc_conv_forward(const icf_conv_args* a, cudaStream_t stream);
 int icf_ws_conv_forward(const icf_conv_args* a, cudaStream_t stream);
 // implemented in icf_conv_sc.cu (scatter-form transposed conv, few output channels); same return convention
 int icf_sc_conv_forward(const icf_conv_args* a, cudaStream_t stream);
+// implemented in icf_conv_cm.cu (unit-stride first layer, channel-major accumulator); same return convention
+int icf_cm_conv_forward(const icf_conv_args* a, cudaStream_t stream);
 int icf_launch_col_stats(const void* y, int ydt, int ypitch, int64_t pixels, int C, float* stats, cudaStream_t st);
 int icf_tc_conv_wgrad(const icf_wgrad_args* a, cudaStream_t stream);
