@@ -321,7 +321,7 @@ def run_ours(args):
     import torch.distributed as dist
     from icf_b200 import ops, synth
     from icf_b200.arch import FAMILIES, forward_flops_per_image
-    from icf_b200.trainer import BiGANTrainer, counterfactual
+    from icf_b200.trainer import BiGANTrainer, counterfactual, counterfactual_stream
     fam = args.family
     mod = importlib.import_module(f"image_scms.{fam}")
     H, W = FAMILIES[fam].image
@@ -529,12 +529,9 @@ def run_ours(args):
             ms_cf = timed(lambda: counterfactual(E, G, d_img, d_c0, d_c1, out=outb), 5)
 
             def cf_e2e():
-                d_img.copy_(h_img, non_blocking=True)
-                for k in d_c0:
-                    d_c0[k].copy_(h_c0[k], non_blocking=True)
-                    d_c1[k].copy_(h_c1[k], non_blocking=True)
-                counterfactual(E, G, d_img, d_c0, d_c1, out=outb)
-                h_res.copy_(outb, non_blocking=True)
+                # host batch -> counterfactual images on the host through the public streamed call: chunks of 8192 images,
+                # H2D / kernels / D2H on three streams (every byte still crosses inside the timed region)
+                counterfactual_stream(E, G, h_img, h_c0, h_c1, out=h_res, chunk=8192)
                 torch.cuda.current_stream().synchronize()
 
             cf_e2e()
@@ -545,7 +542,8 @@ def run_ours(args):
             cf = {"metric": "counterfactual_images_per_s", "value": world * nb / (ms_cf * 1e-3), "unit": "images/s",
                   "batch_per_gpu": nb, "ms": ms_cf,
                   "e2e": {"value": world * nb / (ms_cf_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": cf_h2d,
-                          "d2h_bytes_per_step": h_res.numel() * 4, "ms": ms_cf_e2e},
+                          "d2h_bytes_per_step": h_res.numel() * 4, "ms": ms_cf_e2e,
+                          "api": "icf_b200.trainer.counterfactual_stream (8192-image chunks, copies overlapped)"},
                   "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks()["tf_sust"], "unit": "TFLOP/s",
                                "frac": tf / peaks()["tf_sust"], "traffic": None,
                                "algorithmic_flops": cf_flops, "what": "F_E + F_G valid-tap FLOPs of the whole pipeline / its time"},

@@ -295,3 +295,60 @@ def counterfactual(E, G, x: torch.Tensor, c: Dict[str, torch.Tensor], c_cf: Dict
             out = torch.empty((N, 1, exE.H, exE.W), dtype=torch.float32, device=exE.device)
         ops.cast(img.ptr, img.code, out.data_ptr(), ops.code_of(out), out.numel())
     return out
+
+
+def counterfactual_stream(E, G, x: torch.Tensor, c: Dict[str, torch.Tensor], c_cf: Dict[str, torch.Tensor],
+                          out: Optional[torch.Tensor] = None, chunk: int = 8192):
+    """``counterfactual`` for HOST-resident batches (the scoring scripts hold the test set on the host,
+    mnist_bigan_score.py:79-96): the batch is cut into chunks and moved through a three-stage pipeline — host->device copy of
+    chunk j+1 and device->host copy of chunk j-1 run on their own streams while chunk j is encoded and decoded — so the
+    end-to-end rate approaches the device rate instead of copy + compute + copy (418 MB per 65536 MorphoMNIST images
+    against 15 ms of kernels).  ``x`` / attribute tensors / ``out`` should be pinned for the copies to be asynchronous; images
+    are independent, so the result equals the one-shot call bit for bit."""
+    exE = E.engine()
+    dev = exE.device
+    H, W = exE.H, exE.W
+    xh = x.reshape(-1, H * W)
+    nb = xh.shape[0]
+    if out is None:
+        out = torch.empty((nb, 1, H, W), dtype=torch.float32).pin_memory()
+    oh = out.reshape(nb, H * W)
+    chunk = max(1, min(chunk, nb))
+    with torch.cuda.device(dev):
+        cur = torch.cuda.current_stream()
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        bufs = []
+        for _ in range(2):
+            bufs.append({"x": torch.empty((chunk, H * W), dtype=xh.dtype, device=dev),
+                         "c": {k: torch.empty((chunk,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev) for k, v in c.items()},
+                         "cf": {k: torch.empty((chunk,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev) for k, v in c_cf.items()},
+                         "o": torch.empty((chunk, 1, H, W), dtype=torch.float32, device=dev),
+                         "in": torch.cuda.Event(), "comp": torch.cuda.Event(), "out": torch.cuda.Event()})
+        s_in.wait_stream(cur)
+        s_out.wait_stream(cur)
+        for j, lo in enumerate(range(0, nb, chunk)):
+            hi = min(nb, lo + chunk)
+            n = hi - lo
+            b = bufs[j & 1]
+            with torch.cuda.stream(s_in):
+                if j >= 2:
+                    s_in.wait_event(b["comp"])                       # the kernels that read this input buffer are done
+                b["x"][:n].copy_(xh[lo:hi], non_blocking=True)
+                for k in c:
+                    b["c"][k][:n].copy_(c[k][lo:hi], non_blocking=True)
+                for k in c_cf:
+                    b["cf"][k][:n].copy_(c_cf[k][lo:hi], non_blocking=True)
+                b["in"].record(s_in)
+            cur.wait_event(b["in"])
+            if j >= 2:
+                cur.wait_event(b["out"])                             # this output buffer has been copied out
+            counterfactual(E, G, b["x"][:n], {k: v[:n] for k, v in b["c"].items()}, {k: v[:n] for k, v in b["cf"].items()},
+                           out=b["o"][:n])
+            b["comp"].record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(b["comp"])
+                oh[lo:hi].copy_(b["o"][:n].reshape(n, H * W), non_blocking=True)
+                b["out"].record(s_out)
+        cur.wait_stream(s_out)
+        cur.wait_stream(s_in)
+    return out

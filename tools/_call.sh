@@ -1,1 +1,1 @@
-for i in 1 2; do timeout 600 python -m pytest tests/test_gpu_modules.py -m gpu -q -s -k "test_autograd_vs_oracle" 2>&1 | grep -E "max err" | sed 's/cancelling.*//' | cut -c1-200; done
+for i in 1 2 3; do timeout 600 python -m pytest tests/test_gpu_next.py -m gpu -q -x -k "explain or stream" 2>&1 | tail -2; done
