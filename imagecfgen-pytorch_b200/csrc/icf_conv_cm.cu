@@ -66,8 +66,10 @@ __device__ __forceinline__ uint64_t desc_interleaved(uint32_t saddr, uint32_t lb
   return d;
 }
 
-// FAST: K = 32 = out_pitch, LeakyReLU with 0 <= slope <= 1, 16-byte aligned destination (D.dx.1)
-template <bool FAST>
+// FAST: K = out_pitch in {32, 64, 128}, LeakyReLU with 0 <= slope <= 1 (or no activation = slope 1), 16-byte aligned destination
+// (D.dx.1 forward; the data gradient of the generator's one-channel tail)
+// PLAIN (with FAST): no bias, activation, mask or statistics — a data gradient: the tile is only converted and transposed
+template <bool FAST, bool PLAIN>
 __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                 const __grid_constant__ CmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_con
     const int sub = e >> 2, nsub = CM_EPI_WARPS / 4;
     const int m = q4 * 32 + lane;
     const int j = m / p.K, k = m - j * p.K;
+    const int kb = k - lane;                            // FAST (K a multiple of 32): first channel of this warp's 32
     const float bias = p.bias ? p.bias[k] : 0.f;
     const int i_lo = (sub * p.NI) / nsub, i_hi = ((sub + 1) * p.NI) / nsub;
     const int cpi = (p.Q + 31) >> 5;                    // 32-column units per image
@@ -216,24 +219,32 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_con
           uint32_t pk[4];
 #pragma unroll
           for (int t = 0; t < 8; t += 2) {
-            float f0 = __uint_as_float(v[g8 + t]) + bias, f1 = __uint_as_float(v[g8 + t + 1]) + bias;
-            if (FAST) {                                                          // LeakyReLU, 0 <= slope <= 1: max(x, slope*x)
-              f0 = fmaxf(f0, f0 * slope);
-              f1 = fmaxf(f1, f1 * slope);
-            } else {
-              f0 = icf::apply_act(f0, act, slope);
-              f1 = icf::apply_act(f1, act, slope);
+            float f0 = __uint_as_float(v[g8 + t]), f1 = __uint_as_float(v[g8 + t + 1]);
+            if (!PLAIN) {
+              f0 += bias;
+              f1 += bias;
+              if (FAST) {                                                        // LeakyReLU, 0 <= slope <= 1: max(x, slope*x)
+                f0 = fmaxf(f0, f0 * slope);
+                f1 = fmaxf(f1, f1 * slope);
+              } else {
+                f0 = icf::apply_act(f0, act, slope);
+                f1 = icf::apply_act(f1, act, slope);
+              }
+              f0 *= mkv;
+              f1 *= mkv;
             }
-            pk[t >> 1] = pack_bf16(f0 * mkv, f1 * mkv);
+            pk[t >> 1] = pack_bf16(f0, f1);
           }
           if (y < p.P) {
             const bool whole = g8 + 8 <= nv;
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-              const float r = __uint_as_float((t & 1) ? (pk[t >> 1] & 0xFFFF0000u) : (pk[t >> 1] << 16));   // the value AS STORED
-              if (whole || g8 + t < nv) {
-                ssum += r;
-                ssq = fmaf(r, r, ssq);
+              if (!PLAIN) {
+                const float r = __uint_as_float((t & 1) ? (pk[t >> 1] & 0xFFFF0000u) : (pk[t >> 1] << 16));   // the value AS STORED
+                if (whole || g8 + t < nv) {
+                  ssum += r;
+                  ssq = fmaf(r, r, ssq);
+                }
               }
               const uint16_t h = (uint16_t)((t & 1) ? (pk[t >> 1] >> 16) : (pk[t >> 1] & 0xFFFFu));
               if (FAST) {
@@ -245,11 +256,11 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_con
           }
         }
         if (FAST) {
-          // K = 32 = out_pitch: the warp's lanes are the 32 channels of ONE output row; the [pixel][32 ch] tile leaves as
-          // 16-byte stores, 512 contiguous bytes per instruction
+          // K = out_pitch, a multiple of 32: the warp's lanes are 32 consecutive channels of ONE output row; the [pixel][32 ch]
+          // tile leaves as 16-byte stores (K = 32: 512 contiguous bytes per instruction)
           __syncwarp();
           if (y < p.P) {
-            uint8_t* og = reinterpret_cast<uint8_t*>(p.dst + (((int64_t)n * p.P + y) * p.Q + c0) * 32);
+            uint8_t* og = reinterpret_cast<uint8_t*>(p.dst + (((int64_t)n * p.P + y) * p.Q + c0) * p.K + kb);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
               const int px = (lane >> 2) + 8 * r;
@@ -257,7 +268,7 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_con
                 uint4 w;
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
                              : "r"(tile_rd + (uint32_t)(r * 512)) : "memory");
-                *reinterpret_cast<uint4*>(og + (size_t)px * 64 + (size_t)(lane & 3) * 16) = w;
+                *reinterpret_cast<uint4*>(og + (size_t)px * (size_t)(2 * p.K) + (size_t)(lane & 3) * 16) = w;
               }
             }
           }
@@ -355,16 +366,20 @@ int icf_cm_conv_forward(const icf_conv_args* a, cudaStream_t st) {
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICF_REQUIRE(r == CUDA_SUCCESS, "first-layer conv: cuTensorMapEncodeTiled failed (%d)", (int)r);
   }
-  const bool fast = a->K == 32 && a->out_pitch == 32 && a->act == ICF_ACT_LRELU && a->slope >= 0.f && a->slope <= 1.f &&
-                    (reinterpret_cast<uintptr_t>(a->dst) & 15) == 0;
-  static icf::SmemGuard guard_f, guard_g;
-  if (int r = fast ? guard_f.ensure(reinterpret_cast<const void*>(conv_cm_kernel<true>), smem, "first-layer conv")
-                   : guard_g.ensure(reinterpret_cast<const void*>(conv_cm_kernel<false>), smem, "first-layer conv"))
+  const bool fast = (a->K & 31) == 0 && a->out_pitch == a->K && (reinterpret_cast<uintptr_t>(a->dst) & 15) == 0 &&
+                    ((a->act == ICF_ACT_LRELU && a->slope >= 0.f && a->slope <= 1.f) || a->act == ICF_ACT_NONE);
+  if (fast && a->act == ICF_ACT_NONE) p.slope = 1.f;            // max(x, 1*x) = x
+  const bool plain = fast && a->act == ICF_ACT_NONE && !a->bias && !a->out_mask && !a->stats;
+  static icf::SmemGuard guard_f, guard_g, guard_p;
+  if (int r = plain ? guard_p.ensure(reinterpret_cast<const void*>(conv_cm_kernel<true, true>), smem, "first-layer conv")
+              : fast ? guard_f.ensure(reinterpret_cast<const void*>(conv_cm_kernel<true, false>), smem, "first-layer conv")
+                     : guard_g.ensure(reinterpret_cast<const void*>(conv_cm_kernel<false, false>), smem, "first-layer conv"))
     return r;
   const int sms = icf::sm_count();
   const int64_t items = (int64_t)p.img_groups * p.row_blocks;
   const int grid = items < sms ? (int)items : sms;
-  if (fast) conv_cm_kernel<true><<<grid, CM_THREADS, smem, st>>>(mx, p);
-  else conv_cm_kernel<false><<<grid, CM_THREADS, smem, st>>>(mx, p);
+  if (plain) conv_cm_kernel<true, true><<<grid, CM_THREADS, smem, st>>>(mx, p);
+  else if (fast) conv_cm_kernel<true, false><<<grid, CM_THREADS, smem, st>>>(mx, p);
+  else conv_cm_kernel<false, false><<<grid, CM_THREADS, smem, st>>>(mx, p);
   return icf::check_launch("conv_cm");
 }

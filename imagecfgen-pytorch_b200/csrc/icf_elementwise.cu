@@ -358,13 +358,23 @@ __global__ void act_backward_fewc_kernel(const icf_actbwd_args a) {
   float sb[4] = {0.f, 0.f, 0.f, 0.f};
   for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < a.pixels; pix += (int64_t)gridDim.x * blockDim.x) {
     const int64_t n = sample_of(pix, a.pixels_per_sample);
+    float gv[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c = 0; c < a.C; ++c) {
       float g = icf::ld_any(a.dOut, a.d_dtype, pix * a.d_pitch + c);
       const float yv = icf::ld_any(a.y, a.y_dtype, pix * a.y_pitch + c);
       if (a.out_mask) g *= a.out_mask[n * a.mask_pitch + c];
       g *= icf::act_grad_from_output(yv, a.act, a.slope);
-      icf::st_any(a.dPre, a.p_dtype, pix * a.p_pitch + c, g);
+      gv[c] = g;
       sb[c] += g;
+    }
+    if (a.p_dtype == ICF_BF16 && a.p_pitch == 8) {
+      // the whole 16-byte pixel in one store, pitch padding as ZEROS: consumers that reduce over the padded pixel (the
+      // channel-major conv kernel reads the raw 8-channel rows) must never meet uninitialised memory there
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(gv[0], gv[1]), p1 = __floats2bfloat162_rn(gv[2], gv[3]);
+      uint4 w = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), 0u, 0u);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dPre) + pix * 8) = w;
+    } else {
+      for (int c = 0; c < a.C; ++c) icf::st_any(a.dPre, a.p_dtype, pix * a.p_pitch + c, gv[c]);
     }
   }
   if (a.dbias) {

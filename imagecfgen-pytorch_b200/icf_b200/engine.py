@@ -264,6 +264,15 @@ class LayerExec:
                             self.S, self.stride, self.pad, None, "none", 0.0, ops.ptr(dx.t, dx.off + self.head_lo), dx.code,
                             dx.pitch)
             return
+        if self.px8 and dx.pitch == self.Cin and dpre.pitch == 8 and self.wb_pitch == 8:
+            # data gradient of the one-channel stride-1 ConvTranspose2d tail = a unit-stride conv over the 16-byte pixels of
+            # dpre: w_bwd [Cin][R*S][8] IS the folded (win = S) packing [Cin][R][S*8], so the channel-major first-layer
+            # kernel serves it (icf_conv_cm.cu)
+            ops.conv_forward(self.code, ops.GATHER, N, self.P, self.Q, self.S * 8, 8, self.Hin, self.Win,
+                             self.Cin, dx.pitch, self.R, 1, 1, 0, dpre.ptr, self.w_bwd.data_ptr(), self.Cin,
+                             self.S * 8, dx.ptr, win=self.S, alg_flops=self.alg_flops_img * N,
+                             alg_bytes=self.alg_bytes_img * N)
+            return
         form = ops.TRANSPOSED if self.form == ops.GATHER else ops.GATHER
         lin = self.spec.kind == "linear"
         dp_pitch = dpre.pitch * self.Hout * self.Wout if lin else dpre.pitch
