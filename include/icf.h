@@ -39,7 +39,8 @@ int icf_version(void);
 int icf_tc_enabled(void);
 void icf_set_tc_enabled(int on);
 /* Kernel family the calling thread's last icf_conv_forward used: 0 SIMT fp32 FMA, 1 per-tap tcgen05 implicit GEMM,
- * 2 weight-stationary row-streaming tcgen05 kernel, 3 scatter-form tcgen05 kernel (<= 8 output channels), -1 none yet (tests and profiles assert the intended path). */
+ * 2 weight-stationary row-streaming tcgen05 kernel, 3 scatter-form tcgen05 kernel (<= 8 output channels), 4 channel-major
+ * tcgen05 kernel (folded unit-stride layers on 16-byte pixels), -1 none yet (tests and profiles assert the intended path). */
 enum { ICF_PATH_SIMT = 0, ICF_PATH_TC = 1, ICF_PATH_WS = 2, ICF_PATH_SC = 3, ICF_PATH_CM = 4 };
 int icf_last_conv_path(void);
 
