@@ -40,6 +40,7 @@ constexpr int CM_ACC_COLS = 256;
 struct CmParams {
   int N, H, W, P, Q, K, R;
   int JB, D, KS;                          // output rows per block, source rows per block, 16-element K-steps of the window
+  int stride;
   int NI, ncols;                          // images per item, MMA N = NI*W
   int row_blocks, img_groups;
   int w_pitch, out_pitch, mask_pitch;
@@ -69,7 +70,9 @@ __device__ __forceinline__ uint64_t desc_interleaved(uint32_t saddr, uint32_t lb
 // FAST: K = out_pitch in {32, 64, 128}, LeakyReLU with 0 <= slope <= 1 (or no activation = slope 1), 16-byte aligned destination
 // (D.dx.1 forward; the data gradient of the generator's one-channel tail)
 // PLAIN (with FAST): no bias, activation, mask or statistics — a data gradient: the tile is only converted and transposed
-template <bool FAST, bool PLAIN>
+// SX: conv stride (1 or 2).  Stride 2 runs the x direction as a unit-stride conv over ALL input pixels (the window of pixel n starts 16 bytes
+// after that of pixel n-1 whatever the stride is) and the epilogue reads every second accumulator column; the source rows step by 2.
+template <bool FAST, bool PLAIN, int SX>
 __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                 const __grid_constant__ CmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_con
     const int total = p.D * 128 * chunks;
     for (int idx = threadIdx.x; idx < total; idx += CM_THREADS) {
       const int c = idx % chunks, m = (idx / chunks) & 127, d = idx / (chunks * 128);
-      const int j = m / p.K, k = m - j * p.K, r = d - j;
+      const int j = m / p.K, k = m - j * p.K, r = d - p.stride * j;
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (r >= 0 && r < p.R && c * 8 < p.w_pitch)
         v = *reinterpret_cast<const uint4*>(p.w + ((int64_t)k * p.R + r) * p.w_pitch + c * 8);
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_con
     int s = 0;
     uint32_t ph = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
-      const int ig = it / p.row_blocks, y0 = (it - ig * p.row_blocks) * p.JB;
+      const int ig = it / p.row_blocks, y0 = (it - ig * p.row_blocks) * p.JB * p.stride;     // first source row
       mbar_wait(empty_bar(s), ph ^ 1);
       mbar_expect_tx_if(full_bar(s), (uint32_t)p.D * p.d_bytes, leader);
       tma_load_4d_if(smem_base + ring_off + (uint32_t)s * p.stage_bytes, &map_x, full_bar(s), 0, 0, ig * p.NI, y0, leader);
@@ -180,7 +183,8 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_con
     const int kb = k - lane;                            // FAST (K a multiple of 32): first channel of this warp's 32
     const float bias = p.bias ? p.bias[k] : 0.f;
     const int i_lo = (sub * p.NI) / nsub, i_hi = ((sub + 1) * p.NI) / nsub;
-    const int cpi = (p.Q + 31) >> 5;                    // 32-column units per image
+    constexpr int UO = 32 / SX;                         // output pixels per 32-column unit
+    const int cpi = (p.Q + UO - 1) / UO;                // units per image
     const int act = p.act;
     const float slope = p.slope;
     float ssum = 0.f, ssq = 0.f;
@@ -204,22 +208,22 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_con
 #pragma unroll 1
       for (int u = 0; u < n_img * cpi; ++u) {
         uint32_t v[32];
-        tmem_ld16(tacc + (uint32_t)(il * p.W + c0), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        if (c0 + 16 < p.Q) tmem_ld16(tacc + (uint32_t)(il * p.W + c0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        const int nv = p.Q - c0 < UO ? p.Q - c0 : UO;                            // valid output pixels of this unit
+        tmem_ld16(tacc + (uint32_t)(il * p.W + SX * c0), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        if (SX * nv > 16) tmem_ld16(tacc + (uint32_t)(il * p.W + SX * c0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
         float mkv = mk[0];
 #pragma unroll
         for (int t = 1; t < CM_MAX_IMG; ++t) mkv = il == t ? mk[t] : mkv;
-        const int nv = p.Q - c0 < 32 ? p.Q - c0 : 32;                            // valid pixels of this unit
         const int n = n_lo + il;
         tmem_ld_wait();
         if (FAST) __syncwarp();                                                  // the previous unit's tile has been read
 #pragma unroll
-        for (int g8 = 0; g8 < 32; g8 += 8) {
+        for (int g8 = 0; g8 < UO; g8 += 8) {
           if (g8 >= nv) break;                                                   // warp-uniform: unused accumulator columns
           uint32_t pk[4];
 #pragma unroll
           for (int t = 0; t < 8; t += 2) {
-            float f0 = __uint_as_float(v[g8 + t]), f1 = __uint_as_float(v[g8 + t + 1]);
+            float f0 = __uint_as_float(v[SX * (g8 + t)]), f1 = __uint_as_float(v[SX * (g8 + t + 1)]);
             if (!PLAIN) {
               f0 += bias;
               f1 += bias;
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_con
             }
           }
         }
-        c0 += 32;
+        c0 += UO;
         if (c0 >= p.Q) { c0 = 0; ++il; }
       }
       tc_fence_before();
@@ -308,25 +312,26 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
 
 // returns 0 = launched, -1 = not this kernel's case, >0 = error
 int icf_cm_conv_forward(const icf_conv_args* a, cudaStream_t st) {
-  if (a->dtype != ICF_BF16 || a->form != ICF_FORM_GATHER || a->win < 2 || a->S != 1 || a->stride != 1 || a->pad != 0) return -1;
+  if (a->dtype != ICF_BF16 || a->form != ICF_FORM_GATHER || a->win < 2 || a->S != 1 || (a->stride != 1 && a->stride != 2) || a->pad != 0) return -1;
   if (a->in_pitch != 8 || a->out_f32 || a->accumulate) return -1;
   if (a->K < 16 || a->K > 128 || (128 % a->K) || a->out_pitch < a->K) return -1;
   if (a->w_pitch & 7) return -1;
   if ((reinterpret_cast<uintptr_t>(a->src) & 15) || (reinterpret_cast<uintptr_t>(a->w) & 15)) return -1;
-  if (a->P + a->R - 1 > a->H || a->Q + a->win - 1 > a->W) return -1;
+  if ((a->P - 1) * a->stride + a->R > a->H || (a->Q - 1) * a->stride + a->win > a->W) return -1;
   static const int mode = []() { const char* e = getenv("ICF_CM"); return e && e[0] ? atoi(e) : 1; }();   // 0 off, 2 = swapped strides (debug)
   if (mode == 0) return -1;
   CmParams p;
   memset(&p, 0, sizeof(p));
   p.N = a->N; p.H = a->H; p.W = a->W; p.P = a->P; p.Q = a->Q; p.K = a->K; p.R = a->R;
   p.JB = 128 / a->K;
-  p.D = p.JB + a->R - 1;
+  p.stride = a->stride;
+  p.D = a->stride * (p.JB - 1) + a->R;
   p.KS = (a->win * 8 + 15) / 16;
   if (p.D > 12 || p.KS > 4 || a->W > 128) return -1;
   // images per item: MMA N = NI*W <= 256, multiple of 16
   p.NI = 0;
   for (int ni = 256 / a->W; ni >= 1; --ni)                                     // (the epilogue reads whole 16-column groups)
-    if ((ni * a->W) % 16 == 0 && (ni - 1) * a->W + (a->Q + 31) / 32 * 32 <= 256 && ni <= CM_MAX_IMG * (CM_EPI_WARPS / 4)) { p.NI = ni; break; }
+    if ((ni * a->W) % 16 == 0 && (ni - 1) * a->W + (a->stride * a->Q + 31) / 32 * 32 <= 256 && ni <= CM_MAX_IMG * (CM_EPI_WARPS / 4)) { p.NI = ni; break; }
   if (p.NI == 0 || p.NI * a->W < 64) return -1;
   p.ncols = p.NI * a->W;
   p.row_blocks = icf::cdiv(a->P, p.JB);
@@ -369,17 +374,20 @@ int icf_cm_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   const bool fast = (a->K & 31) == 0 && a->out_pitch == a->K && (reinterpret_cast<uintptr_t>(a->dst) & 15) == 0 &&
                     ((a->act == ICF_ACT_LRELU && a->slope >= 0.f && a->slope <= 1.f) || a->act == ICF_ACT_NONE);
   if (fast && a->act == ICF_ACT_NONE) p.slope = 1.f;            // max(x, 1*x) = x
-  const bool plain = fast && a->act == ICF_ACT_NONE && !a->bias && !a->out_mask && !a->stats;
-  static icf::SmemGuard guard_f, guard_g, guard_p;
-  if (int r = plain ? guard_p.ensure(reinterpret_cast<const void*>(conv_cm_kernel<true, true>), smem, "first-layer conv")
-              : fast ? guard_f.ensure(reinterpret_cast<const void*>(conv_cm_kernel<true, false>), smem, "first-layer conv")
-                     : guard_g.ensure(reinterpret_cast<const void*>(conv_cm_kernel<false, false>), smem, "first-layer conv"))
+  if (a->stride == 2 && !fast) return -1;
+  const bool plain = fast && a->stride == 1 && a->act == ICF_ACT_NONE && !a->bias && !a->out_mask && !a->stats;
+  static icf::SmemGuard guard_f, guard_g, guard_p, guard_2;
+  if (int r = a->stride == 2 ? guard_2.ensure(reinterpret_cast<const void*>(conv_cm_kernel<true, false, 2>), smem, "first-layer conv")
+              : plain ? guard_p.ensure(reinterpret_cast<const void*>(conv_cm_kernel<true, true, 1>), smem, "first-layer conv")
+              : fast ? guard_f.ensure(reinterpret_cast<const void*>(conv_cm_kernel<true, false, 1>), smem, "first-layer conv")
+                     : guard_g.ensure(reinterpret_cast<const void*>(conv_cm_kernel<false, false, 1>), smem, "first-layer conv"))
     return r;
   const int sms = icf::sm_count();
   const int64_t items = (int64_t)p.img_groups * p.row_blocks;
   const int grid = items < sms ? (int)items : sms;
-  if (plain) conv_cm_kernel<true, true><<<grid, CM_THREADS, smem, st>>>(mx, p);
-  else if (fast) conv_cm_kernel<true, false><<<grid, CM_THREADS, smem, st>>>(mx, p);
-  else conv_cm_kernel<false, false><<<grid, CM_THREADS, smem, st>>>(mx, p);
+  if (a->stride == 2) conv_cm_kernel<true, false, 2><<<grid, CM_THREADS, smem, st>>>(mx, p);
+  else if (plain) conv_cm_kernel<true, true, 1><<<grid, CM_THREADS, smem, st>>>(mx, p);
+  else if (fast) conv_cm_kernel<true, false, 1><<<grid, CM_THREADS, smem, st>>>(mx, p);
+  else conv_cm_kernel<false, false, 1><<<grid, CM_THREADS, smem, st>>>(mx, p);
   return icf::check_launch("conv_cm");
 }

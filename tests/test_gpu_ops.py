@@ -167,20 +167,21 @@ def test_conv_wgrad_first_layer_folded(case):
 
 
 @pytest.mark.parametrize("case", [(6, 5, 28, 32, 5), (300, 5, 28, 32, 5), (1200, 5, 28, 32, 5), (37, 7, 20, 64, 3), (33, 3, 24, 32, 4),
-                                  (10, 5, 30, 128, 5)], ids=lambda c: str(c))
+                                  (10, 5, 30, 128, 5), (300, 5, 30, 64, 3, 2), (45, 3, 22, 64, 5, 2)], ids=lambda c: str(c))
 def test_conv_forward_first_layer_folded(case):
     """Unit-stride first-layer forward on the 8-channel-pitch feature tensor in the folded ("win") packing (the form
     engine.LayerExec uses for D.dx.1) with bias, LeakyReLU, Dropout2d mask and BatchNorm statistics in the epilogue:
-    channel-major accumulator kernel (icf_conv_cm.cu; ragged image groups and row blocks included)."""
+    channel-major accumulator kernel (icf_conv_cm.cu; ragged image groups and row blocks included; stride 2 = E.layers.0)."""
     ops = ops_mod()
-    N, C, H, K, k = case
+    N, C, H, K, k = case[:5]
+    st = case[5] if len(case) > 5 else 1
     g = torch.Generator().manual_seed(6)
     x = torch.randn(N, C, H, H, generator=g).bfloat16().float()
     w = (torch.randn(K, C, k, k, generator=g) / (C * k * k) ** 0.5).bfloat16().float()
     b = torch.randn(K, generator=g)
     mask = (torch.rand(N, K, generator=g) > 0.2).float() / 0.8
-    P = H - k + 1
-    ref = F.leaky_relu(F.conv2d(x.double(), w.double(), b.double(), 1, 0), 0.1) * mask.double().reshape(N, K, 1, 1)
+    P = (H - k) // st + 1
+    ref = F.leaky_relu(F.conv2d(x.double(), w.double(), b.double(), st, 0), 0.1) * mask.double().reshape(N, K, 1, 1)
     xt = nhwc(x, 8, torch.bfloat16)
     wf = torch.zeros(K * k * 64, dtype=torch.bfloat16, device=DEV)
     wsrc = w.contiguous().to(DEV)
@@ -189,7 +190,7 @@ def test_conv_forward_first_layer_folded(case):
     y = torch.full((N * P * P, kp), 7.0, dtype=torch.bfloat16, device=DEV)
     stats = torch.zeros(2, K, dtype=torch.float32, device=DEV)
     md, bias = mask.to(DEV), b.to(DEV)
-    ops.conv_forward(1, ops.GATHER, N, H, H, k * 8, 8, P, P, K, kp, k, 1, 1, 0, xt.data_ptr(), wf.data_ptr(), K, 64,
+    ops.conv_forward(1, ops.GATHER, N, H, H, k * 8, 8, P, P, K, kp, k, 1, st, 0, xt.data_ptr(), wf.data_ptr(), K, 64,
                      y.data_ptr(), bias=bias.data_ptr(), act="lrelu", slope=0.1, mask=md.data_ptr(), mask_pitch=K,
                      stats=stats.data_ptr(), win=k)
     torch.cuda.synchronize()
