@@ -130,7 +130,7 @@ class HingeLossCFExplainer:
         m = (x - x_cf).abs().flatten(1).mean(dim=1)
         return (self.c * h + m).sum(), h, m
 
-    def explain(self, x: torch.Tensor, attrs: Dict[str, torch.Tensor], target_class=None, train_z=True, steps=30, lr=0.1,
+    def explain(self, x: torch.Tensor, attrs: Dict[str, torch.Tensor], target_class=None, train_z=True, steps=30, lr=0.1, *,
                 init: Optional[Dict[str, torch.Tensor]] = None, graph=False, history: Optional[list] = None, optimise_z=False):
         """-> x_cf (B,1,H,W).  ``init``: starting raw rows per optimised attribute (+ 'z'), default = upstream's random draw;
         ``graph``: capture one step as a CUDA graph and replay it; ``history``: list receiving (hinge, rec) per step.

@@ -32,8 +32,9 @@ def test_struct_layouts_match_header_sizes():
     src = r'''
 #include <stdio.h>
 #include "icf.h"
-int main(){printf("%zu %zu %zu %zu %zu %zu\n", sizeof(icf_conv_args), sizeof(icf_wgrad_args), sizeof(icf_perm),
- sizeof(icf_imgfeat_args), sizeof(icf_latfeat_args), sizeof(icf_actbwd_args));return 0;}'''
+int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(icf_conv_args), sizeof(icf_wgrad_args), sizeof(icf_perm),
+ sizeof(icf_imgfeat_args), sizeof(icf_latfeat_args), sizeof(icf_actbwd_args), sizeof(icf_explain_group), sizeof(icf_scm_affine_args),
+ sizeof(icf_pack_job));return 0;}'''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
@@ -42,7 +43,7 @@ int main(){printf("%zu %zu %zu %zu %zu %zu\n", sizeof(icf_conv_args), sizeof(icf
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = list(map(int, subprocess.check_output([exe]).split()))
     mine = [ctypes.sizeof(t) for t in (lib.ConvArgs, lib.WgradArgs, lib.Perm, lib.ImgFeatArgs, lib.LatFeatArgs,
-                                       lib.ActBwdArgs)]
+                                       lib.ActBwdArgs, lib.ExplainGroup, lib.ScmAffineArgs, lib.PackJob)]
     assert mine == sizes, (mine, sizes)
 
 
@@ -406,6 +407,37 @@ def test_train_signatures_match_the_reference():
         pos = [p.name for p in sig.parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]
         assert pos == names, (fam, pos)
         assert all(p.kind == p.KEYWORD_ONLY for p in sig.parameters.values() if p.name not in names)
+
+
+def test_explainer_signatures_and_layout_match_the_reference():
+    """explain/cf_example.py:18-34,83-103: constructor / explain() positional parameters of the two explainers under the reference's
+    import path (our additions are keyword-only), and the flat raw-row layout of the hinge explainer: upstream's dict order, the
+    ignored attributes absent, the latent row last, 16-byte aligned groups."""
+    import inspect
+    from explain.cf_example import DeepCounterfactualExplainer, HingeLossCFExplainer, hinge, max_excluding, mse  # noqa: F401
+    from icf_b200 import explain as X
+
+    def pos(fn):
+        ps = list(inspect.signature(fn).parameters.values())
+        assert all(p.kind == p.KEYWORD_ONLY for p in ps if p.kind != p.POSITIONAL_OR_KEYWORD)
+        return [p.name for p in ps if p.kind == p.POSITIONAL_OR_KEYWORD]
+    assert pos(DeepCounterfactualExplainer.__init__) == ["self", "encoder", "decoder", "classifier", "target_feature"]
+    assert pos(DeepCounterfactualExplainer.explain) == ["self", "x", "attrs", "target_class", "sample_points", "metric"]
+    assert pos(HingeLossCFExplainer.__init__) == ["self", "encoder", "decoder", "classifier", "target_feature", "latent_dim",
+                                                  "categorical_features", "features_to_ignore", "c"]
+    assert pos(HingeLossCFExplainer.explain) == ["self", "x", "attrs", "target_class", "train_z", "steps", "lr"]
+    d = inspect.signature(HingeLossCFExplainer.explain).parameters
+    assert (d["target_class"].default, d["train_z"].default, d["steps"].default, d["lr"].default) == (None, True, 30, 0.1)
+    assert inspect.signature(HingeLossCFExplainer.__init__).parameters["c"].default == 10.0
+    ex = HingeLossCFExplainer(None, None, None, "digit", 512, categorical_features=["digit"], features_to_ignore=["slant"])
+    attrs = {"thickness": torch.zeros(3, 1), "intensity": torch.zeros(3, 1), "slant": torch.zeros(3, 1), "digit": torch.zeros(3, 10)}
+    specs, n = ex._layout(attrs, 3, True)
+    assert [(k, m, w) for k, m, w, _ in specs] == [("thickness", X.TANH, 1), ("intensity", X.TANH, 1), ("digit", X.SOFTMAX, 10),
+                                                  ("z", X.TANH, 512)]
+    offs = [o for *_, o in specs]
+    assert offs == [0, 4, 8, 40] and all(o % 4 == 0 for o in offs) and n == 40 + 3 * 512
+    assert float(max_excluding(torch.tensor([[1.0, 5.0, 3.0], [9.0, 2.0, 4.0]]), torch.tensor([1, 0]))[0]) == 3.0
+    assert torch.equal(max_excluding(torch.tensor([[1.0, 5.0, 3.0], [9.0, 2.0, 4.0]]), 0), torch.tensor([5.0, 4.0]))
 
 
 class _TinyNet(torch.nn.Module):
