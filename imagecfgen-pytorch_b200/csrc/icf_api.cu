@@ -127,6 +127,20 @@ int icf_conv_forward(const icf_conv_args* a, void* stream) {
   return icf_simt_conv_forward(a, st);
 }
 
+int64_t icf_workspace_bytes(const char* entry_point, const void* /*args*/) {
+  static const char* const names[] = {
+      "icf_conv_forward", "icf_conv_wgrad", "icf_pack", "icf_unpack", "icf_pack4", "icf_unpack4", "icf_pack_multi", "icf_unpack_multi",
+      "icf_argmax_rows", "icf_image_features_fwd", "icf_image_features_bwd", "icf_latent_features_fwd", "icf_latent_features_bwd",
+      "icf_bn_finalize", "icf_scale_shift_mask", "icf_bn_bwd_reduce", "icf_act_backward", "icf_bce_logits", "icf_sigmoid_mean",
+      "icf_adam_step", "icf_mse_loss", "icf_col_mean", "icf_latent_l2", "icf_scm_affine_cf", "icf_onehot_swap",
+      "icf_explain_transform", "icf_explain_backward", "icf_log_spectrogram", "icf_spect_stats", "icf_spect_to_img",
+      "icf_col2im_taps", "icf_im2col_taps", "icf_bn_fold_weights", "icf_bn_fold_wgrad", "icf_cast", "icf_fill_f32"};
+  if (!entry_point) return -1;
+  for (const char* n : names)
+    if (strcmp(n, entry_point) == 0) return 0;   // shared / tensor memory staging only, accumulators are explicit arguments
+  return -1;
+}
+
 int icf_conv_wgrad(const icf_wgrad_args* a, void* stream) {
   ICF_REQUIRE(a, "icf_conv_wgrad: null args");
   ICF_REQUIRE(a->dtype == ICF_F32 || a->dtype == ICF_BF16, "icf_conv_wgrad: dtype %d", a->dtype);

@@ -140,6 +140,7 @@ _SIGS = {
     "icf_im2col_taps": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "icf_bn_fold_weights": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "icf_bn_fold_wgrad": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "icf_workspace_bytes": (_i64, [C.c_char_p, _vp]),
     "icf_cast": (_i32, [_vp, _i32, _vp, _i32, _i64, _vp]),
     "icf_fill_f32": (_i32, [_vp, _f32, _i64, _vp]),
 }

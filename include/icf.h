@@ -411,6 +411,13 @@ int icf_explain_backward(const float* out, float* draw, const icf_explain_group*
 int icf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float* state /*[8]*/, void* stream);
 
+/* Workspace query of SURVEY.md §8(b): bytes of scratch memory the entry point named `entry_point` ("icf_conv_forward",
+ * "icf_conv_wgrad", ...) would need for the given argument struct (may be NULL).  Every kernel of this library keeps its
+ * staging buffers in shared / tensor memory and takes its accumulators (dw, stats, loss_out) as explicit arguments, so the
+ * answer is 0 for every entry point; -1 for a name the library does not export.  Kept so that a binding written against
+ * the survey's contract can size (and skip) its workspace allocation. */
+int64_t icf_workspace_bytes(const char* entry_point, const void* args);
+
 /* small utilities */
 int icf_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
 int icf_fill_f32(float* dst, float value, int64_t n, void* stream);

@@ -24,6 +24,8 @@ def test_abi_exports_every_declared_symbol():
     assert not missing, missing
     assert set(lib.EXPORTED_SYMBOLS) == declared
     assert lib.load().icf_version() == 1
+    # no entry point needs a hidden workspace (SURVEY §8b query): 0 for every exported kernel entry, -1 for an unknown name
+    assert lib.load().icf_workspace_bytes(b"icf_conv_forward", None) == 0 and lib.load().icf_workspace_bytes(b"nope", None) == -1
 
 
 def test_struct_layouts_match_header_sizes():
