@@ -1,10 +1,8 @@
-(time python bench.py) > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err; tail -4 gpurun_out/r02_bench_final.err
-(time python bench.py --impl reference --steps 3 --warmup 1) > gpurun_out/r02_bench_ref.json 2> gpurun_out/r02_bench_ref.err; tail -4 gpurun_out/r02_bench_ref.err; cut -c1-400 gpurun_out/r02_bench_ref.json
-for f in audio_mnist whalecalls esrf_acoustic; do
-python bench.py --family $f --steps 5 --warmup 3 --skip-cpu --skip-torch > gpurun_out/r02_bench_$f.json 2> gpurun_out/r02_bench_$f.err; tail -1 gpurun_out/r02_bench_$f.err; cp gpurun_out/per_layer_$f.json gpurun_out/r02_per_layer_$f.json 2>/dev/null
-python - <<PY
-import json
-d=json.load(open("gpurun_out/r02_bench_$f.json"))
-print("$f", {k:d[k] for k in ("value","ms_per_step")}, d["roofline"]["frac"], d.get("counterfactual",{}).get("value"))
-PY
-done
+export SKIP_LIST=1
+export KERNELS="conv_cm_kernel<.bool.1,..bool.0,..int.1> conv_cm_kernel<.bool.1,..bool.1 conv_cm_kernel<.bool.1,..bool.0,..int.2>"
+bash tools/profile_round.sh r02i
+CMD="python bench.py --steps 2 --warmup 3 --skip-cf --skip-cpu --skip-torch --no-graph"
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 2000 -c 1400 --csv \
+    --log-file gpurun_out/launches_dram_r02i.csv $CMD > gpurun_out/ncu_list_dram_i.log 2>&1
+echo "rc=$?"; wc -l gpurun_out/launches_dram_r02i.csv
+python -m pytest tests -m gpu -q -x 2>&1 | tail -2
