@@ -192,11 +192,14 @@ int encode_plain(CUtensorMap* m, const void* base, int rank, const cuuint64_t* d
 // ------------------------------------------------------------------------------------------------------------------------
 constexpr int PS_ISSUERS = 4;
 constexpr int PS_THREADS = 32 * (1 + PS_ISSUERS + 4);
-constexpr int PS_SLOTS = 6;
+constexpr int PS_MAX_SLOTS = 16;         // ring depth is chosen at launch (as many ~10 KB items as fit ~190 KB).  Depth 6 -> 16 changed nothing
+                                         // (104 us): the issuers wait on `full` because the dY boxes arrive as one TMA request per 64-byte row
+                                         // (16 k requests per SM and launch, ~8 cycles each) — the kernel is TMA-request bound, not latency bound
 
 struct PsParams {
   int N, P, A, R, B;
   int JB, D, pblocks, ksteps, QP, W;
+  int slots;                             // ring depth
   uint32_t swb;                          // bytes per dY row = A*2 (64 or 128) = swizzle span
   uint32_t dy_bytes, x_row_bytes, slot_bytes;
   uint32_t n_cols, tmem_cols;
@@ -208,17 +211,17 @@ __global__ void __launch_bounds__(PS_THREADS, 1) wgrad_px8s_kernel(const __grid_
                                                                    const __grid_constant__ PsParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)PS_SLOTS * p.slot_bytes + 4096);   // 4 KB read-past guard
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PS_SLOTS + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.slots * p.slot_bytes + 4096);   // 4 KB read-past guard
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PS_MAX_SLOTS + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (PS_SLOTS + s); };
-  const uint32_t done_bar = bar_base + 8u * (2 * PS_SLOTS);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (PS_MAX_SLOTS + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * PS_MAX_SLOTS);
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_dy);
     prefetch_tmap(&map_x);
-    for (int s = 0; s < PS_SLOTS; ++s) {
+    for (int s = 0; s < p.slots; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), PS_ISSUERS);
     }
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) wgrad_px8s_kernel(const __grid_
   }
   // the X windows of the last reduction rows run past their row (into the next one, the next slot or the guard): whatever
   // lies there is multiplied by the zero-filled q >= Q part of dY, but it has to be finite from the first MMA on
-  for (uint32_t i = threadIdx.x; i < ((uint32_t)PS_SLOTS * p.slot_bytes + 4096u) / 16u; i += PS_THREADS)
+  for (uint32_t i = threadIdx.x; i < ((uint32_t)p.slots * p.slot_bytes + 4096u) / 16u; i += PS_THREADS)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 1) tmem_alloc_rt(smem_u32(tmem_slot), p.tmem_cols);
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) wgrad_px8s_kernel(const __grid_
       const uint32_t base = smem_base + (uint32_t)s * p.slot_bytes;
       tma_load_4d_if(base, &map_dy, full_bar(s), 0, 0, p0, n, leader);                 // rows beyond P / q beyond Q arrive as zeros
       tma_load_3d_if(base + p.dy_bytes, &map_x, full_bar(s), 0, p0, n, leader);
-      if (++s == PS_SLOTS) { s = 0; ph ^= 1; }
+      if (++s == p.slots) { s = 0; ph ^= 1; }
     }
   } else if (warp <= PS_ISSUERS) {
     const int wi = warp - 1;
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) wgrad_px8s_kernel(const __grid_
       }
       first = 1u;
       umma_commit_if(empty_bar(s), leader);
-      if (++s == PS_SLOTS) { s = 0; ph ^= 1; }
+      if (++s == p.slots) { s = 0; ph ^= 1; }
     }
     umma_commit_if(done_bar, leader);
   } else {
@@ -355,7 +358,10 @@ int launch_px8s(const icf_wgrad_args* a, cudaStream_t st) {
   p.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
   // the widest read past an X row: reduction row QP-1, column group n_cols/8-1
   if ((uint32_t)(p.QP + (int)p.n_cols / 8) * 16u > p.x_row_bytes + 4096u) return -1;
-  const size_t smem = (size_t)PS_SLOTS * p.slot_bytes + 4096 + 1024 + 256;
+  p.slots = (int)((190u * 1024u) / p.slot_bytes);
+  if (p.slots > PS_MAX_SLOTS) p.slots = PS_MAX_SLOTS;
+  if (p.slots < 2) return -1;
+  const size_t smem = (size_t)p.slots * p.slot_bytes + 4096 + 1024 + 512;
   if (smem > 225 * 1024) return -1;
   p.dw = a->dw;
   CUtensorMap mdy, mx;
