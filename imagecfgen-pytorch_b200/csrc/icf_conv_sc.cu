@@ -233,10 +233,11 @@ int launch_sc(const CUtensorMap& ma, const CUtensorMap& mw, const ScParams& p, i
 // (x0-4 .. x0+15; TMA zero-fills the columns outside the image).  The epilogue only slides the R output rows: K*R adds
 // per source row, no shuffles; every lane stores its own pixel.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int SX_XT = 16, SX_PAD = 4, SX_IMGS = 8, SX_SLOTS = 6;   // output columns per tile, halo slots, images, ring
+constexpr int SX_XT = 16, SX_PAD = 4, SX_IMGS = 8, SX_SLOTS = 6;   // output columns per tile, halo slots, images, ring (even: slot parity = row parity)
+constexpr int SX_THREADS = SC_THREADS + 32;                        // + a second MMA-issuing warp (warp 6)
 
 template <int R, int S, int KT>
-__global__ void __launch_bounds__(SC_THREADS, 1) conv_sx_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(SX_THREADS, 1) conv_sx_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_w,
                                                                 const __grid_constant__ ScParams p) {
   constexpr uint32_t SLOT_BYTES = (SX_XT + SX_PAD) * SX_IMGS * 128, SLOT_TX = SLOT_BYTES;
@@ -299,10 +300,14 @@ __global__ void __launch_bounds__(SC_THREADS, 1) conv_sx_kernel(const __grid_con
       }
       if (dbg_on && lane == 0) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = w0; }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 6) {
     {
       // the whole warp runs the issue loop and one elected lane issues: inside an `if (lane == 0)` region every
-      // tcgen05.mma costs ~190 cycles of warp time (measured), in warp-uniform code ~90
+      // tcgen05.mma costs ~190 cycles of warp time (measured), in warp-uniform code ~90.  TWO issuing warps: the kernel is
+      // bound by that issue cost (ncu: the epilogue warps wait on acc_full for half of their samples, tensor pipe 12 %; ten
+      // MMAs of 128 x 48 x 16 per source row) — warp 1 issues the even source rows into accumulator 0, warp 6 the odd ones into
+      // accumulator 1 (slot parity = row parity because the ring has an even number of slots).
+      const uint32_t wi = warp == 1 ? 0u : 1u;
       const uint32_t leader = elect_one();
       const uint32_t idesc = make_idesc(128, p.NR, 0, 0);
       const uint64_t d0 = make_desc(0, 16, 1024);
@@ -311,26 +316,28 @@ __global__ void __launch_bounds__(SC_THREADS, 1) conv_sx_kernel(const __grid_con
       tc_fence_after();
       int sl = 0;
       uint32_t ph = 0;
-      uint32_t g = 0;                                   // source rows issued so far
+      uint32_t g = 0;                                   // source rows issued so far (by both warps)
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x)
         for (int y = 0; y < p.H; ++y, ++g) {
           const uint32_t buf = g & 1u;
-          SX_WAIT(w0, acc_empty(buf), ((g >> 1) & 1u) ^ 1u);
-          SX_WAIT(w1, full_bar(sl), ph);
-          tc_fence_after();
-          const uint32_t slot = smem_u32(slots) + (uint32_t)sl * SLOT_BYTES;
+          if (buf == wi) {
+            SX_WAIT(w0, acc_empty(buf), ((g >> 1) & 1u) ^ 1u);
+            SX_WAIT(w1, full_bar(sl), ph);
+            tc_fence_after();
+            const uint32_t slot = smem_u32(slots) + (uint32_t)sl * SLOT_BYTES;
 #pragma unroll 1
-          for (int s = 0; s < S; ++s) {
-            const uint32_t a_lo = (((slot + (uint32_t)(SX_PAD - s) * 1024u) >> 4) & 0x3FFFu) | desc_lo;
-            const uint32_t b_lo = (((smem_u32(wtile) + (uint32_t)s * p.wblk) >> 4) & 0x3FFFu) | desc_lo;
-            for (int k = 0; k < p.kdepth; ++k)
-              umma_bf16_lo(tmem_base + buf * SC_ACC_COLS, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (s | k) ? 1u : 0u, leader);
+            for (int s = 0; s < S; ++s) {
+              const uint32_t a_lo = (((slot + (uint32_t)(SX_PAD - s) * 1024u) >> 4) & 0x3FFFu) | desc_lo;
+              const uint32_t b_lo = (((smem_u32(wtile) + (uint32_t)s * p.wblk) >> 4) & 0x3FFFu) | desc_lo;
+              for (int k = 0; k < p.kdepth; ++k)
+                umma_bf16_lo(tmem_base + buf * SC_ACC_COLS, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (s | k) ? 1u : 0u, leader);
+            }
+            umma_commit_if(empty_bar(sl), leader);
+            umma_commit_if(acc_full(buf), leader);
           }
-          umma_commit_if(empty_bar(sl), leader);
-          umma_commit_if(acc_full(buf), leader);
           if (++sl == SX_SLOTS) { sl = 0; ph ^= 1; }
         }
-      if (dbg_on && lane == 0) { p.dbg[2] = clock64() - t_begin; p.dbg[3] = w0; p.dbg[4] = w1; }
+      if (dbg_on && lane == 0 && wi == 0) { p.dbg[2] = clock64() - t_begin; p.dbg[3] = w0; p.dbg[4] = w1; }
     }
   } else {
     // ===== epilogue: TMEM lane m = x_local*8 + image; every thread owns one output column of one image =====
@@ -428,7 +435,7 @@ template <int R, int S, int KT>
 int launch_sx(const CUtensorMap& ma, const CUtensorMap& mw, const ScParams& p, int grid, size_t smem, cudaStream_t st) {
   static icf::SmemGuard guard;
   if (int r = guard.ensure(reinterpret_cast<const void*>(conv_sx_kernel<R, S, KT>), smem, "scatter-form conv")) return r;
-  conv_sx_kernel<R, S, KT><<<grid, SC_THREADS, smem, st>>>(ma, mw, p);
+  conv_sx_kernel<R, S, KT><<<grid, SX_THREADS, smem, st>>>(ma, mw, p);
   return icf::check_launch("conv_sx");
 }
 
