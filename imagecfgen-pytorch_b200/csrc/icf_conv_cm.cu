@@ -34,7 +34,7 @@ using namespace icf_tc;
 constexpr int CM_STAGES = 3;
 constexpr int CM_EPI_WARPS = 16;
 constexpr int CM_MAX_IMG = 4;                           // images per epilogue warp and item
-constexpr int CM_THREADS = 32 * (2 + CM_EPI_WARPS);     // warp 0 TMA, warp 1 MMA (owns TMEM), 16 epilogue warps
+constexpr int CM_THREADS = 32 * (3 + CM_EPI_WARPS);     // warp 0 TMA, warp 1 MMA (owns TMEM), 16 epilogue warps, last warp = second MMA issuer
 constexpr int CM_ACC_COLS = 256;
 
 struct CmParams {
@@ -137,7 +137,9 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_con
       tma_load_4d_if(smem_base + ring_off + (uint32_t)s * p.stage_bytes, &map_x, full_bar(s), 0, 0, ig * p.NI, y0, leader);
       if (++s == CM_STAGES) { s = 0; ph ^= 1; }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == CM_EPI_WARPS + 2) {
+    // two issuing warps, one accumulator each: even items from warp 1, odd items from the last warp
+    const uint32_t wi = warp == 1 ? 0u : 1u;
     const uint32_t leader = elect_one();
     const uint32_t idesc = make_idesc(128, p.ncols, 0, 0);
     const uint32_t chunks = 2u * (uint32_t)p.KS;
@@ -146,11 +148,15 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_con
     const uint32_t a_hi = (uint32_t)(dA >> 32), a_lo0 = (uint32_t)dA;
     const uint32_t b_hi = (uint32_t)(dB >> 32), b_lo0 = (uint32_t)dB;
     const uint32_t a16 = (smem_base >> 4) & 0x3FFFu;
-    int s = 0, buf = 0;
-    uint32_t ph = 0, aph = 0;                                 // bit b = phase of accumulator b
-    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    int s = 0;
+    uint32_t ph = 0, aph = 0, buf = 0;                        // aph: phase of this warp's accumulator
+    for (int it = blockIdx.x; it < items; it += gridDim.x, buf ^= 1u) {
+      if (buf != wi) {
+        if (++s == CM_STAGES) { s = 0; ph ^= 1; }
+        continue;
+      }
       mbar_wait(full_bar(s), ph);
-      mbar_wait(acc_empty(buf), ((aph >> buf) & 1u) ^ 1u);
+      mbar_wait(acc_empty(buf), aph ^ 1u);
       tc_fence_after();
       const uint32_t b16 = ((smem_base + ring_off + (uint32_t)s * p.stage_bytes) >> 4) & 0x3FFFu;
       const uint32_t acc = tmem_base + (uint32_t)buf * CM_ACC_COLS;
@@ -163,8 +169,7 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_con
       }
       umma_commit_if(empty_bar(s), leader);
       umma_commit_if(acc_full(buf), leader);
-      aph ^= 1u << buf;
-      buf ^= 1;
+      aph ^= 1u;
       if (++s == CM_STAGES) { s = 0; ph ^= 1; }
     }
   } else {
