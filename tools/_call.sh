@@ -1,6 +1,13 @@
-timeout 300 python -m pytest tests/test_gpu_ops.py -m gpu -q -x -k "first_layer_folded" 2>&1 | tail -2
-for v in "ICF_CM_DBG=0" "ICF_CM_DBG=1"; do
-echo "--- $v"; env $v timeout 300 python tools/layer_bench.py --family mnist --batch 4096 --only "Dx.dx.1" --passes fwd 2>&1 | grep "dx.1 "
-done
-timeout 300 python tools/layer_bench.py --family mnist --batch 4096 --only "E.layers.0" --passes fwd 2>&1 | grep "layers.0 "
-timeout 300 python tools/layer_bench.py --family mnist --batch 4096 --only "G.layers.8" --passes dgrad 2>&1 | grep "layers.8 "
+python bench.py > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err; tail -2 gpurun_out/r02_bench_final.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/r02_bench_final.json"))
+print({k:d[k] for k in ("value","ms_per_step")}, d["e2e"]["value"], d["roofline"]["frac"], d["roofline"]["layer_rows_at_or_above_half_roofline"], d["counterfactual"]["value"], d["counterfactual"]["e2e"]["value"], d["cudnn_baseline"]["bf16_cl"]["value"], d["cpu_baseline"]["value"])
+PY
+export SKIP_LIST=1
+export KERNELS="conv_cm_kernel<.bool.1,..bool.0,..int.1> conv_sx_kernel"
+bash tools/profile_round.sh r02j
+CMD="python bench.py --steps 2 --warmup 3 --skip-cf --skip-cpu --skip-torch --no-graph"
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 2000 -c 1400 --csv \
+    --log-file gpurun_out/launches_dram_r02j.csv $CMD > gpurun_out/ncu_list_dram_j.log 2>&1
+echo "rc=$?"
