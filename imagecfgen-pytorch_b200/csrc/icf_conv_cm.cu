@@ -33,7 +33,7 @@ using namespace icf_tc;
 
 constexpr int CM_STAGES = 3;
 constexpr int CM_EPI_WARPS = 16;
-constexpr int CM_MAX_IMG = 4;                           // images per epilogue warp and item
+constexpr int CM_MAX_IMG = 4;                           // 32-column units per epilogue warp and item
 constexpr int CM_THREADS = 32 * (3 + CM_EPI_WARPS);     // warp 0 TMA, warp 1 MMA (owns TMEM), 16 epilogue warps, last warp = second MMA issuer
 constexpr int CM_ACC_COLS = 256;
 
@@ -187,9 +187,16 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_con
     const int j = m / p.K, k = m - j * p.K;
     const int kb = k - lane;                            // FAST (K a multiple of 32): first channel of this warp's 32
     const float bias = p.bias ? p.bias[k] : 0.f;
-    const int i_lo = (sub * p.NI) / nsub, i_hi = ((sub + 1) * p.NI) / nsub;
     constexpr int UO = 32 / SX;                         // output pixels per 32-column unit
     const int cpi = (p.Q + UO - 1) / UO;                // units per image
+    const int units = p.NI * cpi;                       // units of an item: dealt round-robin to the nsub warps of a lane quarter
+    int il_of[CM_MAX_IMG], c0_of[CM_MAX_IMG];           // (a wide image is ONE image per item: its row is split over the warps)
+#pragma unroll
+    for (int t = 0; t < CM_MAX_IMG; ++t) {
+      const int u = sub + t * nsub;
+      il_of[t] = u < units ? u / cpi : -1;
+      c0_of[t] = u < units ? (u - (u / cpi) * cpi) * UO : 0;
+    }
     const int act = p.act;
     const float slope = p.slope;
     float ssum = 0.f, ssq = 0.f;
@@ -199,26 +206,29 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_con
     uint32_t aph = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       const int ig = it / p.row_blocks, y = (it - ig * p.row_blocks) * p.JB + j;
-      const int n_lo = ig * p.NI + i_lo;
-      int n_img = i_hi - i_lo;
-      if (n_img > p.N - n_lo) n_img = p.N - n_lo;
-      if (p.dbg == 1) n_img = 0;
+      const int n_lo = ig * p.NI;
       float mk[CM_MAX_IMG];
 #pragma unroll
-      for (int t = 0; t < CM_MAX_IMG; ++t) mk[t] = (p.mask && t < n_img) ? p.mask[(int64_t)(n_lo + t) * p.mask_pitch + k] : 1.f;
+      for (int t = 0; t < CM_MAX_IMG; ++t)
+        mk[t] = (p.mask && il_of[t] >= 0 && n_lo + il_of[t] < p.N) ? p.mask[(int64_t)(n_lo + il_of[t]) * p.mask_pitch + k] : 1.f;
       mbar_wait(acc_full(buf), (aph >> buf) & 1u);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)buf * CM_ACC_COLS + (uint32_t)(i_lo * p.W);
-      int il = 0, c0 = 0;
+      const uint32_t tacc = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)buf * CM_ACC_COLS;
 #pragma unroll 1
-      for (int u = 0; u < n_img * cpi; ++u) {
+      for (int ut = 0; ut < CM_MAX_IMG; ++ut) {
+        int il = il_of[0], c0 = c0_of[0];
+        float mkv = mk[0];
+#pragma unroll
+        for (int t = 1; t < CM_MAX_IMG; ++t) {
+          il = ut == t ? il_of[t] : il;
+          c0 = ut == t ? c0_of[t] : c0;
+          mkv = ut == t ? mk[t] : mkv;
+        }
+        if (il < 0 || n_lo + il >= p.N || p.dbg == 1) break;                     // warp-uniform (units are dealt in image order)
         uint32_t v[32];
         const int nv = p.Q - c0 < UO ? p.Q - c0 : UO;                            // valid output pixels of this unit
         tmem_ld16(tacc + (uint32_t)(il * p.W + SX * c0), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
         if (SX * nv > 16) tmem_ld16(tacc + (uint32_t)(il * p.W + SX * c0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-        float mkv = mk[0];
-#pragma unroll
-        for (int t = 1; t < CM_MAX_IMG; ++t) mkv = il == t ? mk[t] : mkv;
         const int n = n_lo + il;
         tmem_ld_wait();
         if (FAST) __syncwarp();                                                  // the previous unit's tile has been read
@@ -282,8 +292,6 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const __grid_con
             }
           }
         }
-        c0 += UO;
-        if (c0 >= p.Q) { c0 = 0; ++il; }
       }
       tc_fence_before();
       __syncwarp();
@@ -332,13 +340,20 @@ int icf_cm_conv_forward(const icf_conv_args* a, cudaStream_t st) {
   p.stride = a->stride;
   p.D = a->stride * (p.JB - 1) + a->R;
   p.KS = (a->win * 8 + 15) / 16;
-  if (p.D > 12 || p.KS > 4 || a->W > 128) return -1;
+  if (p.D > 12 || p.KS > 4) return -1;
   // images per item: MMA N = NI*W <= 256, multiple of 16
   p.NI = 0;
-  for (int ni = 256 / a->W; ni >= 1; --ni)                                     // (the epilogue reads whole 16-column groups)
-    if ((ni * a->W) % 16 == 0 && (ni - 1) * a->W + (a->stride * a->Q + 31) / 32 * 32 <= 256 && ni <= CM_MAX_IMG * (CM_EPI_WARPS / 4)) { p.NI = ni; break; }
-  if (p.NI == 0 || p.NI * a->W < 64) return -1;
+  const int cpi = (a->stride * a->Q + 31) / 32;                                // 32-column epilogue units per image
+  for (int ni = 256 / a->W; ni >= 1; --ni)                                     // (the epilogue reads whole 32-column units)
+    if ((ni * a->W) % 16 == 0 && (ni - 1) * a->W + cpi * 32 <= 256 && ni * cpi <= CM_MAX_IMG * (CM_EPI_WARPS / 4)) { p.NI = ni; break; }
   p.ncols = p.NI * a->W;
+  if (p.NI == 0 && cpi * 32 <= 256 && cpi <= CM_MAX_IMG * (CM_EPI_WARPS / 4)) {
+    // a wide image (the 130- and 258-pixel rows of the spectrogram families): ONE image per item, the accumulator columns are the
+    // pixels of its row up to the last window start; the windows of the last columns run into the next source row (finite data)
+    p.NI = 1;
+    p.ncols = ((a->stride * (a->Q - 1) + 1) + 15) & ~15;
+  }
+  if (p.NI == 0 || p.ncols < 64 || p.ncols > 256) return -1;
   p.row_blocks = icf::cdiv(a->P, p.JB);
   p.img_groups = icf::cdiv(a->N, p.NI);
   p.w_pitch = a->w_pitch; p.out_pitch = a->out_pitch; p.mask_pitch = a->mask_pitch;
