@@ -127,9 +127,19 @@ int icf_conv_forward(const icf_conv_args* a, void* stream) {
   return icf_simt_conv_forward(a, st);
 }
 
+int icf_conv_forward_splitk(const icf_conv_args* a, float* partial, int64_t partial_elems, void* stream) {
+  if (int r = validate_conv(a)) return r;
+  if (a->N == 0) return 0;
+  if (partial && partial_elems > 0 && a->dtype == ICF_BF16 && icf_tc_enabled() && !a->accumulate && !a->stats) {
+    int r = icf_tc_conv_forward_splitk(a, icf::as_stream(stream), partial, partial_elems);
+    if (r >= 0) { icf::g_conv_path = ICF_PATH_TC; return r; }
+  }
+  return icf_conv_forward(a, stream);
+}
+
 int64_t icf_workspace_bytes(const char* entry_point, const void* /*args*/) {
   static const char* const names[] = {
-      "icf_conv_forward", "icf_conv_wgrad", "icf_pack", "icf_unpack", "icf_pack4", "icf_unpack4", "icf_pack_multi", "icf_unpack_multi",
+      "icf_conv_forward", "icf_conv_forward_splitk", "icf_conv_wgrad", "icf_pack", "icf_unpack", "icf_pack4", "icf_unpack4", "icf_pack_multi", "icf_unpack_multi",
       "icf_argmax_rows", "icf_image_features_fwd", "icf_image_features_bwd", "icf_latent_features_fwd", "icf_latent_features_bwd",
       "icf_bn_finalize", "icf_scale_shift_mask", "icf_bn_bwd_reduce", "icf_act_backward", "icf_bce_logits", "icf_sigmoid_mean",
       "icf_adam_step", "icf_mse_loss", "icf_col_mean", "icf_latent_l2", "icf_scm_affine_cf", "icf_onehot_swap",

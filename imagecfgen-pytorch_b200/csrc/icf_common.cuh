@@ -104,3 +104,5 @@ int icf_sc_conv_forward(const icf_conv_args* a, cudaStream_t stream);
 int icf_cm_conv_forward(const icf_conv_args* a, cudaStream_t stream);
 int icf_launch_col_stats(const void* y, int ydt, int ypitch, int64_t pixels, int C, float* stats, cudaStream_t st);
 int icf_tc_conv_wgrad(const icf_wgrad_args* a, cudaStream_t stream);
+// per-tap kernel with split-K into a zeroed fp32 scratch (+ finishing pass); -1 when splitting would not help
+int icf_tc_conv_forward_splitk(const icf_conv_args* a, cudaStream_t stream, float* partial, int64_t partial_elems);

@@ -45,6 +45,9 @@ struct TcParams {
   const float* bias;
   const float* mask;
   void* dst;
+  int splits;                   // > 1: the (tap, channel chunk) iterations of a tile are dealt to `splits` work items whose raw fp32
+  float* partial;               //      accumulators are ADDED to partial[pixel][partial_pitch] (bias / activation / mask: splitk_finish_kernel)
+  int partial_pitch;
   TapTable tt;
 };
 
@@ -76,6 +79,12 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t, int ti
   c.i0 = it * p.ti; c.j0 = jt * p.tj; c.n0 = nt * p.tn; c.k0 = kt * tile_n;
   c.inside = c.i0 < c.Pi && c.j0 < c.Qj;     // false: the tile lies outside this (smaller) parity class
   return c;
+}
+
+// split-K: iterations [lo, hi) of the tile's n_iters belong to split sp
+__device__ __forceinline__ void split_range(int n_iters, int sp, int splits, int& lo, int& hi) {
+  lo = (int)(((int64_t)n_iters * sp) / splits);
+  hi = (int)(((int64_t)n_iters * (sp + 1)) / splits);
 }
 
 // a tap is live for a tile when its source box touches the un-padded input
@@ -132,21 +141,30 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
     // ===== TMA producer (warp-uniform loops, the elected lane issues) =====
     const uint32_t leader = elect_one();
     int iter = 0;                                  // ring position, runs on across tiles
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < total_tiles * p.splits; w += gridDim.x) {
+      const int t = w / p.splits, sp = w - t * p.splits;
       const TileCoord c = tile_coord(p, t, TILE_N);
       if (!c.inside) continue;
       const int ntaps = p.tt.ntaps[c.cls];
+      int lo = 0, hi = 0x7fffffff, ii = 0;
+      if (p.splits > 1) {
+        int live = 0;
+        for (int i = 0; i < ntaps; ++i) live += tap_live(p, c, i) ? 1 : 0;
+        split_range(live * p.kchunks, sp, p.splits, lo, hi);
+      }
       for (int ti_ = 0; ti_ < ntaps; ++ti_) {
         if (!tap_live(p, c, ti_)) continue;
         const int y = c.i0 * p.sstep + p.tt.dy[c.cls][ti_], x = c.j0 * p.sstep + p.tt.dx[c.cls][ti_];
         const int wcol = p.tt.tap[c.cls][ti_] * p.w_pitch;
-        for (int kc = 0; kc < p.kchunks; ++kc, ++iter) {
+        for (int kc = 0; kc < p.kchunks; ++kc, ++ii) {
+          if (ii < lo || ii >= hi) continue;
           const int s = iter % STAGES;
           mbar_wait(empty_bar(s), ((iter / STAGES) & 1) ^ 1);
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
           mbar_expect_tx_if(full_bar(s), p.a_tx_bytes + B_BYTES, leader);
           tma_load_4d_if(sa, &map_a, full_bar(s), kc * BLOCK_K, x, y, c.n0, leader);
           tma_load_2d_if(sb, &map_b, full_bar(s), wcol + kc * BLOCK_K, c.k0, leader);
+          ++iter;
         }
       }
     }
@@ -158,13 +176,19 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
     const uint64_t d0 = make_desc(0, 16, 1024);
     const uint32_t desc_hi = (uint32_t)(d0 >> 32), desc_lo = (uint32_t)d0;      // low word without an address
     int iter = 0, done = 0;                        // ring position; tiles this CTA has accumulated so far
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < total_tiles * p.splits; w += gridDim.x) {
+      const int t = w / p.splits, sp = w - t * p.splits;
       const TileCoord c = tile_coord(p, t, TILE_N);
       if (!c.inside) continue;
       const int ntaps = p.tt.ntaps[c.cls];
       int live = 0;
       for (int i = 0; i < ntaps; ++i) live += tap_live(p, c, i) ? 1 : 0;
-      const int n_iters = live * p.kchunks;
+      int n_iters = live * p.kchunks;
+      if (p.splits > 1) {
+        int lo, hi;
+        split_range(n_iters, sp, p.splits, lo, hi);
+        n_iters = hi - lo;
+      }
       const int b_ = ACC == 2 ? (done & 1) : 0;
       const int use = ACC == 2 ? (done >> 1) : done;
       mbar_wait(tmem_empty_bar(b_), (use & 1) ^ 1);          // the epilogue has drained this accumulator (first use: free)
@@ -194,14 +218,20 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
     const int ti_i = rem / p.tj, tj_i = rem - ti_i * p.tj;
     const int esize = p.out_f32 ? 4 : 2;
     int done = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < total_tiles * p.splits; w += gridDim.x) {
+      const int t = w / p.splits, sp = w - t * p.splits;
       const TileCoord c = tile_coord(p, t, TILE_N);
       if (!c.inside) continue;
       const int k0 = c.k0;
       const int ntaps = p.tt.ntaps[c.cls];
       int live = 0;
       for (int i = 0; i < ntaps; ++i) live += tap_live(p, c, i) ? 1 : 0;
-      const int n_iters = live * p.kchunks;
+      int n_iters = live * p.kchunks;
+      if (p.splits > 1) {
+        int lo, hi;
+        split_range(n_iters, sp, p.splits, lo, hi);
+        n_iters = hi - lo;
+      }
       // bias tile -> shared memory (zero where absent / beyond K), visible to the four epilogue warps; the first barrier
       // keeps a fast warp from overwriting the previous tile's bias while a slow one still reads it
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -268,6 +298,17 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
           if (lane == 0) mbar_arrive(tmem_empty_bar(b_));
         }
         if (!valid) continue;
+        if (p.splits > 1) {                                       // raw partial sums; bias / activation / mask in splitk_finish_kernel
+          if (n_iters > 0) {
+            float* o = p.partial + pix * p.partial_pitch + k0 + c0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              if (j < nv)                                         // partial_pitch is padded to the tile, whole groups of 4 exist
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(__uint_as_float(v[j])),
+                             "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
+          }
+          continue;
+        }
         const int nvl = nv < 16 ? nv : 16;
         int npad = (nvl + 7) & ~7;
         if (k0 + c0 + npad > p.out_pitch) npad = nvl;
@@ -449,6 +490,29 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
   if (warp == 1) tmem_dealloc_rt(tmem_base, p.tmem_cols);
 }
 
+// split-K finish: dst = act(partial + bias) * mask (bf16 or fp32), one thread per (pixel, 4 channels)
+__global__ void splitk_finish_kernel(const float* __restrict__ partial, int partial_pitch, int64_t pixels, int pixels_per_sample, int K,
+                                     const float* __restrict__ bias, int act, float slope, const float* __restrict__ mask, int mask_pitch,
+                                     void* dst, int out_pitch, int out_f32) {
+  const int kq = (K + 3) >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pixels * kq; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / kq;
+    const int k0 = (int)(i - pix * kq) * 4;
+    const float4 v4 = *reinterpret_cast<const float4*>(partial + pix * partial_pitch + k0);
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    const float* mrow = mask ? mask + (pix / pixels_per_sample) * mask_pitch : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + j;
+      if (k >= K) break;
+      float f = icf::apply_act(v[j] + (bias ? bias[k] : 0.f), act, slope);
+      if (mrow) f *= mrow[k];
+      if (out_f32) reinterpret_cast<float*>(dst)[pix * out_pitch + k] = f;
+      else reinterpret_cast<__nv_bfloat16*>(dst)[pix * out_pitch + k] = __float2bfloat16_rn(f);
+    }
+  }
+}
+
 template <int TILE_N, int STAGES, int ACC>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int64_t tiles, int ctas_per_sm, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + TILE_N * BLOCK_K * 2) + 1024 + 256 + 1024;
@@ -463,7 +527,9 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, i
 
 }  // namespace
 
-int icf_tc_conv_forward(const icf_conv_args* a, cudaStream_t st) {
+// partial != NULL: split-K allowed — a zeroed fp32 scratch of partial_elems floats ([N*P*Q][K rounded up to the tile]); used when the
+// tile grid alone would leave most SMs idle.  Returns -1 as icf_tc_conv_forward does.
+static int tc_forward_impl(const icf_conv_args* a, cudaStream_t st, float* partial, int64_t partial_elems) {
   // shapes the tensor-core path takes; everything else runs on the direct / SIMT kernels
   if (a->dtype != ICF_BF16 || a->accumulate) return -1;
   // small-channel first / last layers ride the same kernel: TMA zero-fills the missing channels of the 64-wide
@@ -538,8 +604,24 @@ int icf_tc_conv_forward(const icf_conv_args* a, cudaStream_t st) {
     if (tile_n == 256 && (tile_env == 128 || (tile_env != 256 && g256 * 4 < (int64_t)tc_sm_count() * 3))) tile_n = 128;
   }
   p.tiles_k = icf::cdiv(a->K, tile_n);
-  const int64_t grid = (int64_t)p.n_classes * p.tiles_n * p.tiles_i * p.tiles_j * p.tiles_k;
+  int64_t grid = (int64_t)p.n_classes * p.tiles_n * p.tiles_i * p.tiles_j * p.tiles_k;
   if (grid > 0x7FFFFFFF) return -1;
+  p.splits = 1;
+  if (partial && !a->stats) {
+    // split-K: a tile grid much smaller than the machine (the 1024-channel layers of the spectrogram families at batch 32-128:
+    // 2-8 tiles whose K loop walks 9-25 taps x 16 channel chunks of a 10-50 MB weight) is bound by what ONE SM can pull from L2
+    const int64_t max_iters = (int64_t)taps * p.kchunks, cap = (int64_t)tc_sm_count() * 2;
+    const int pitch = p.tiles_k * tile_n;
+    int64_t sp = cap / grid;
+    if (sp > max_iters / 4) sp = max_iters / 4;                    // at least ~4 ring stages per work item
+    if (sp >= 2 && grid * 4 <= (int64_t)tc_sm_count() && (int64_t)a->N * a->P * a->Q * pitch <= partial_elems && (reinterpret_cast<uintptr_t>(partial) & 15) == 0) {
+      p.splits = (int)sp;
+      p.partial = partial;
+      p.partial_pitch = pitch;
+      grid *= sp;
+    }
+  }
+  if (partial && p.splits == 1) return -1;                          // nothing to split: the caller goes through the normal dispatch
 
   CUtensorMap ma, mb;
   {
@@ -574,11 +656,24 @@ int icf_tc_conv_forward(const icf_conv_args* a, cudaStream_t st) {
     default: r = launch_tc<32, 4, 2>(ma, mb, p, grid, 2, st); break;
   }
   if (r) return r;
+  if (p.splits > 1) {
+    const int64_t pixels = (int64_t)a->N * a->P * a->Q, work = pixels * ((a->K + 3) / 4);
+    int64_t blocks = (work + 255) / 256;
+    if (blocks > (int64_t)tc_sm_count() * 8) blocks = (int64_t)tc_sm_count() * 8;
+    splitk_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(p.partial, p.partial_pitch, pixels, a->P * a->Q, a->K, a->bias, a->act, a->slope,
+                                                          a->out_mask, a->mask_pitch, a->dst, a->out_pitch, a->out_f32);
+    return icf::check_launch("splitk_finish");
+  }
   if (a->stats) {
     if (a->out_f32) { icf::set_error("tensor-core conv: BatchNorm statistics need a bf16 destination"); return 1; }
     return icf_launch_col_stats(a->dst, ICF_BF16, a->out_pitch, (int64_t)a->N * a->P * a->Q, a->K, a->stats, st);
   }
   return 0;
+}
+
+int icf_tc_conv_forward(const icf_conv_args* a, cudaStream_t st) { return tc_forward_impl(a, st, nullptr, 0); }
+int icf_tc_conv_forward_splitk(const icf_conv_args* a, cudaStream_t st, float* partial, int64_t partial_elems) {
+  return tc_forward_impl(a, st, partial, partial_elems);
 }
 
 

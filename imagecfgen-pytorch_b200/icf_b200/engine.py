@@ -243,7 +243,17 @@ class LayerExec:
                          self.R, self.S, self.stride, self.pad, x.ptr,
                          self.w_fwd.data_ptr() if w_override is None else w_override, self.Kout,
                          self.wf_pitch, y.ptr, bias=self.bias.data_ptr() if bias_override is None else bias_override,
-                         act=sp.act, slope=sp.slope, out_f32=out_f32, mask=mask, mask_pitch=mask_pitch, stats=stats)
+                         act=sp.act, slope=sp.slope, out_f32=out_f32, mask=mask, mask_pitch=mask_pitch, stats=stats,
+                         partial=self._splitk_scratch(N * self.P * self.Q, self.Kout, self.taps * self.Cin) if stats is None else None)
+
+    def _splitk_scratch(self, pixels, K, reduction):
+        """Zeroed fp32 scratch that lets icf_conv_forward_splitk deal the K loop of a small-grid layer to many CTAs: a few thousand
+        output pixels against a long reduction (the 512..4096-channel layers of the spectrogram families at batch 32-128)."""
+        # (MorphoMNIST never qualifies — its longest reduction is 4608 — so its forward stays bit-reproducible: split-K sums in
+        # float-atomic order)
+        if self.code != BF16 or pixels > 2048 or reduction <= 4608:
+            return None
+        return torch.zeros((pixels, (K + 255) // 256 * 256), dtype=torch.float32, device=self.device)
 
     def dgrad(self, N, dpre: Act, dx: Act):
         """dx[n,h,w,c] = sum_{k,taps} dpre[...]*w  — the other conv form with the transposed operand."""
@@ -278,7 +288,8 @@ class LayerExec:
         dp_pitch = dpre.pitch * self.Hout * self.Wout if lin else dpre.pitch
         ops.conv_forward(self.code, form, N, self.P, self.Q, self.Kout, dp_pitch,
                          self.Hin, self.Win, self.Cin, dx.pitch, self.R, self.S, self.stride, self.pad,
-                         dpre.ptr, self.w_bwd.data_ptr(), self.Cin, self.wb_pitch, dx.ptr)
+                         dpre.ptr, self.w_bwd.data_ptr(), self.Cin, self.wb_pitch, dx.ptr,
+                         partial=None if lin else self._splitk_scratch(N * self.Hin * self.Win, self.Cin, self.taps * self.Kout))
 
     def _im2col_of(self, N, dpre: Act, consume: bool):
         """[N*Hin*Win, TP] tap matrix of the one-channel gradient ``dpre``.  A backward pass calls wgrad, then dgrad, on the same

@@ -102,6 +102,7 @@ _SIGS = {
     "icf_last_conv_path": (_i32, []),
     "icf_ws_plan": (_i32, [C.POINTER(ConvArgs), C.POINTER(C.c_int32), _i32]),
     "icf_conv_forward": (_i32, [C.POINTER(ConvArgs), _vp]),
+    "icf_conv_forward_splitk": (_i32, [C.POINTER(ConvArgs), _vp, _i64, _vp]),
     "icf_conv_wgrad": (_i32, [C.POINTER(WgradArgs), _vp]),
     "icf_wgrad_plan": (_i32, [C.POINTER(WgradArgs), C.POINTER(C.c_int32), _i32]),
     "icf_pack": (_i32, [_vp, _vp, _i32, C.POINTER(Perm), _vp]),

@@ -77,8 +77,8 @@ def valid_taps(form, H, P, R, stride, pad):
 
 def conv_forward(dtype, form, N, H, W, Cc, in_pitch, P, Q, K, out_pitch, R, S, stride, pad,
                  src, w, w_rows, w_pitch, dst, bias=None, act="none", slope=0.0, out_f32=False,
-                 mask=None, mask_pitch=0, stats=None, accumulate=False, win=0, alg_flops=None, alg_bytes=None):
-    """src/w/dst/bias/mask/stats are raw addresses (ints) or None."""
+                 mask=None, mask_pitch=0, stats=None, accumulate=False, win=0, alg_flops=None, alg_bytes=None, partial=None):
+    """src/w/dst/bias/mask/stats are raw addresses (ints) or None; ``partial``: zeroed fp32 scratch tensor that allows split-K."""
     a = _l.ConvArgs(dtype, form, N, H, W, Cc, in_pitch, P, Q, K, out_pitch, R, S, stride, pad,
                     w_rows, w_pitch, ACT[act], slope, 1 if out_f32 else 0, mask_pitch,
                     1 if accumulate else 0, win, src, w, bias, dst, mask, stats)
@@ -93,6 +93,10 @@ def conv_forward(dtype, form, N, H, W, Cc, in_pitch, P, Q, K, out_pitch, R, S, s
         if alg_bytes is not None:
             nb = alg_bytes
         det = f"{'gather' if form == GATHER else 'transp'} {Cc}x{H}x{W}->{K}x{P}x{Q} k{R}s{stride}p{pad}" + (f" win{win}" if win > 1 else "")
+    if partial is not None:
+        _launch("icf_conv_forward", _l.load().icf_conv_forward_splitk, C.byref(a), partial.data_ptr(), partial.numel(), flops=fl,
+                nbytes=nb, detail=det)
+        return
     _launch("icf_conv_forward", _l.load().icf_conv_forward, C.byref(a), flops=fl, nbytes=nb, detail=det)
 
 

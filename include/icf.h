@@ -81,6 +81,12 @@ typedef struct icf_conv_args {
   float* stats;                  /* [2][K]: += sum, += sum of squares of dst values (BatchNorm), or NULL */
 } icf_conv_args;
 int icf_conv_forward(const icf_conv_args* a, void* stream);
+/* Same operation with split-K allowed: `partial` is a ZEROED fp32 scratch of `partial_elems` floats supplied by the caller
+ * (>= N*P*Q * K rounded up to 256).  When the tile grid of the layer alone would leave most SMs idle (a few hundred output pixels
+ * against a 10-50 MB weight: the 1024-channel layers of the spectrogram families at their default batches) the (tap, channel
+ * chunk) iterations of every tile are dealt to several CTAs that add raw fp32 sums into `partial`, and a finishing pass applies
+ * bias / activation / Dropout2d mask.  `partial` is left dirty.  Otherwise (and for stats != NULL) this IS icf_conv_forward. */
+int icf_conv_forward_splitk(const icf_conv_args* a, float* partial, int64_t partial_elems, void* stream);
 
 /* Introspection / test hook, no kernel launch and no GPU needed: the plan the weight-stationary row-streaming kernel
  * would use for `a` (pointers in `a` only need to be 16-byte aligned, they are not dereferenced).  Returns 0 and fills

@@ -203,6 +203,45 @@ def test_conv_forward_first_layer_folded(case):
     assert rel_err(stats[0], gd.sum(dim=(0, 2, 3))) < 1e-4 and rel_err(stats[1], gd.square().sum(dim=(0, 2, 3))) < 1e-4
 
 
+@pytest.mark.parametrize("case", [(32, 1024, 3, 512, 5, 2, 1, "g"), (32, 512, 7, 1024, 5, 2, 1, "g"), (8, 1024, 1, 1024, 1, 1, 0, "g"),
+                                  (8, 1024, 3, 512, 5, 2, 2, "t"), (5, 1024, 3, 200, 3, 1, 0, "g")], ids=lambda c: str(c))
+def test_conv_forward_splitk(case):
+    """icf_conv_forward_splitk: layers whose tile grid is a handful of CTAs (a few hundred output pixels, a long tap x channel
+    reduction: the 512..1024-channel layers of the spectrogram families at batch 32) with bias / activation / mask applied by the
+    finishing pass; gather and transposed form, ragged channel count."""
+    ops = ops_mod()
+    N, C, H, K, k, s, p, form = case
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(N, C, H, H, generator=g).bfloat16().float()
+    b = torch.randn(K, generator=g)
+    mask = (torch.rand(N, K, generator=g) > 0.3).float() / 0.7
+    cp, kp = (C + 7) // 8 * 8, (K + 7) // 8 * 8
+    T = k * k
+    if form == "g":
+        w = (torch.randn(K, C, k, k, generator=g) / (C * k * k) ** 0.5).bfloat16().float()
+        ref = F.leaky_relu(F.conv2d(x.double(), w.double(), b.double(), s, p), 0.2)
+        wt = pack_w(ops, w, 1, cp)
+        fcode = ops.GATHER
+    else:
+        w = (torch.randn(C, K, k, k, generator=g) / (C * k * k / s / s) ** 0.5).bfloat16().float()
+        ref = F.leaky_relu(F.conv_transpose2d(x.double(), w.double(), b.double(), s, p, 1), 0.2)
+        wt = torch.empty(K * T * cp, dtype=torch.bfloat16, device=DEV)
+        wsrc = w.contiguous().to(DEV)
+        ops.pack(wsrc.data_ptr(), wt.data_ptr(), 1, ops.make_perm(K, T, C, T, 1, K * T, d2_pad=cp))
+        fcode = ops.TRANSPOSED
+    ref = ref * mask.double().reshape(N, K, 1, 1)
+    P = ref.shape[-1]
+    xt = nhwc(x, cp, torch.bfloat16)
+    y = torch.full((N * P * P, kp), 7.0, dtype=torch.bfloat16, device=DEV)
+    part = torch.zeros((N * P * P, (K + 255) // 256 * 256), dtype=torch.float32, device=DEV)
+    md, bias = mask.to(DEV), b.to(DEV)
+    ops.conv_forward(1, fcode, N, H, H, C, cp, P, P, K, kp, k, k, s, p, xt.data_ptr(), wt.data_ptr(), K, cp, y.data_ptr(),
+                     bias=bias.data_ptr(), act="lrelu", slope=0.2, mask=md.data_ptr(), mask_pitch=K, partial=part)
+    torch.cuda.synchronize()
+    assert float(part.abs().max()) > 0                           # the split path ran (the scratch is left dirty)
+    assert rel_err(from_nhwc(y, N, P, P, K), ref) < 8e-3
+
+
 def test_argmax_first_max_wins():
     ops = ops_mod()
     x = torch.tensor([[0, 0, 0], [0, 1, 1], [2, 2, 1], [0.5, 0.2, 0.9]], device=DEV)
