@@ -168,7 +168,7 @@ def test_conv_wgrad_first_layer_folded(case):
 
 @pytest.mark.parametrize("case", [(6, 5, 28, 32, 5), (300, 5, 28, 32, 5), (1200, 5, 28, 32, 5), (37, 7, 20, 64, 3), (33, 3, 24, 32, 4),
                                   (10, 5, 30, 128, 5), (300, 5, 30, 64, 3, 2), (45, 3, 22, 64, 5, 2), (9, 7, 130, 64, 5, 2), (3, 2, 258, 64, 5, 2),
-                                  (5, 4, 150, 32, 3, 1)], ids=lambda c: str(c))
+                                  (5, 4, 150, 32, 3, 1), (20, 3, 16, 16, 2, 1)], ids=lambda c: str(c))
 def test_conv_forward_first_layer_folded(case):
     """Unit-stride first-layer forward on the 8-channel-pitch feature tensor in the folded ("win") packing (the form
     engine.LayerExec uses for D.dx.1) with bias, LeakyReLU, Dropout2d mask and BatchNorm statistics in the epilogue:

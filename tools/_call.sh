@@ -1,2 +1,1 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 4 --steps 20 --warmup 5 --skip-cpu --skip-torch --skip-cf > gpurun_out/r02_bench_4gpu_b.json 2> gpurun_out/r02_bench_4gpu_b.err; tail -2 gpurun_out/r02_bench_4gpu_b.err
-grep "^{" gpurun_out/r02_bench_4gpu_b.json | python -c "import json,sys; d=json.loads(sys.stdin.readline()); print({k:d[k] for k in ('value','ms_per_step','n_gpus')}, d['e2e']['value'])"
+timeout 600 python -m pytest tests/test_gpu_ops.py -m gpu -q -x -k "forward_first_layer_folded" 2>&1 | tail -4
