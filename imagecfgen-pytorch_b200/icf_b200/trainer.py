@@ -89,6 +89,7 @@ class BiGANTrainer:
         gs = 1.0 / self.world
         self.stateEG = torch.tensor([0, lr, betas[0], betas[1], eps, gs, 0, 0], dtype=torch.float32, device=self.device)
         self.stateD = self.stateEG.clone()
+        self.stateG = self.stateEG.clone()            # G's segment of optimizer_E steps on its own (same hyper-parameters, same count)
         self.lr, self.betas, self.eps = lr, betas, eps
         self.overlap = overlap_allreduce and self.world > 1
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.overlap else None
@@ -132,9 +133,12 @@ class BiGANTrainer:
                     self.group.all_reduce(b)
                     b /= self.world
 
-    def _adam(self, grp: _FlatGroup, state):
-        ops.adam_step(grp.flat.data_ptr(), grp.grad.data_ptr(), grp.exp_avg.data_ptr(), grp.exp_avg_sq.data_ptr(),
-                      grp.n, state.data_ptr())
+    def _adam(self, grp: _FlatGroup, state, lo=0, hi=None):
+        """Adam over elements [lo, hi) of the flat buffers (Adam is element-wise: optimizer_E over E's and over G's segment with
+        one step counter each is the reference's single torch.optim.Adam over E.parameters() + G.parameters())."""
+        hi = grp.n if hi is None else hi
+        ops.adam_step(ops.ptr(grp.flat, lo), ops.ptr(grp.grad, lo), ops.ptr(grp.exp_avg, lo), ops.ptr(grp.exp_avg_sq, lo),
+                      hi - lo, state.data_ptr())
 
     # ---- one iteration ------------------------------------------------------------------------------
     def step(self, images: torch.Tensor, c: Dict[str, torch.Tensor], z: Optional[torch.Tensor] = None,
@@ -176,6 +180,7 @@ class BiGANTrainer:
         dl2 = torch.empty((N, 1), dtype=torch.float32, device=self.device)
 
         exE.idx_cache = exD.idx_cache = {}            # attribute argmax indices: computed once per step
+        pending_G = None
         with torch.cuda.device(self.device):
             # ---- Phase A: encoder + generator update (mnist.py:224-230) --------------------------------
             if phase_a:
@@ -193,16 +198,16 @@ class BiGANTrainer:
                 _, dzE = exD.discriminator_backward(sD1, Act(dl, 1), None, need_dz=True)
                 dXG, _ = exD.discriminator_backward(sD2, Act(dl2, 1), None, need_dX=True)
                 exE.encoder_backward(stE, Act(dzE, fam.latent), self.gradsE)
-                lo, hi = self.gEG.segment(0, self.n_E)
-                evE = self._allreduce(self.gEG.grad[lo:hi], side=True)
+                loE, hiE = self.gEG.segment(0, self.n_E)
+                evE = self._allreduce(self.gEG.grad[loE:hiE], side=True)        # in flight during G's backward
                 exG.generator_backward(stG, Act(dXG, 1), self.gradsG)
-                lo, hi = self.gEG.segment(self.n_E, len(self.gEG.params))
-                self._allreduce(self.gEG.grad[lo:hi])
+                loG, hiG = self.gEG.segment(self.n_E, len(self.gEG.params))
+                evG = self._allreduce(self.gEG.grad[loG:hiG], side=True)        # in flight during phase B (which needs E, not G)
                 if evE is not None:
                     torch.cuda.current_stream().wait_event(evE)
-                self._adam(self.gEG, self.stateEG)
+                self._adam(self.gEG, self.stateEG, loE, hiE)
                 exE.repack(force=True)
-                exG.repack(force=True)
+                pending_G = (evG, loG, hiG)
                 del stE, stG, sD1, sD2
             # ---- Phase B: discriminator on real pairs (mnist.py:232-236) -------------------------------
             ops.fill_f32(self.gD.grad.data_ptr(), 0.0, self.gD.n)
@@ -215,6 +220,12 @@ class BiGANTrainer:
             evB = self._allreduce(self.gD.grad, side=True)
             # ---- Phase C: discriminator on generated pairs (mnist.py:237-241) --------------------------
             # G(z) of phase C does not depend on D: it runs while phase B's gradient all-reduce is in flight on the side stream
+            if pending_G is not None:                 # G's half of optimizer_E.step(): its gradient wave had phase B to arrive
+                evG, loG, hiG = pending_G
+                if evG is not None:
+                    torch.cuda.current_stream().wait_event(evG)
+                self._adam(self.gEG, self.stateG, loG, hiG)
+                exG.repack(force=True)
             xG, _ = exG.generator_forward(N, zp, F32, fam.latent, c, save=False)
             if evB is not None:
                 torch.cuda.current_stream().wait_event(evB)

@@ -35,12 +35,12 @@ def to_dev(c):
 
 def _snapshot(tr):
     return [t.clone() for t in (tr.gEG.flat, tr.gEG.exp_avg, tr.gEG.exp_avg_sq, tr.gD.flat, tr.gD.exp_avg, tr.gD.exp_avg_sq,
-                                tr.stateEG, tr.stateD)] + [b.clone() for b in tr.D.buffers()]
+                                tr.stateEG, tr.stateD, tr.stateG)] + [b.clone() for b in tr.D.buffers()]
 
 
 def _restore(tr, snap):
     dst = [tr.gEG.flat, tr.gEG.exp_avg, tr.gEG.exp_avg_sq, tr.gD.flat, tr.gD.exp_avg, tr.gD.exp_avg_sq, tr.stateEG,
-           tr.stateD] + list(tr.D.buffers())
+           tr.stateD, tr.stateG] + list(tr.D.buffers())
     for d, s in zip(dst, snap):
         d.copy_(s)
     for ex in (tr.exE, tr.exG, tr.exD):
