@@ -1,2 +1,3 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29577 bench.py --gpus 8 --steps 20 --warmup 5 --skip-cpu --skip-torch --skip-cf > gpurun_out/r02_bench_8gpu.json 2> gpurun_out/r02_bench_8gpu.err; tail -1 gpurun_out/r02_bench_8gpu.err
-grep "^{" gpurun_out/r02_bench_8gpu.json | python -c "import json,sys; d=json.loads(sys.stdin.readline()); print({k:d[k] for k in ('value','ms_per_step','n_gpus')}, d['e2e']['value'])"
+# scratch command file of the build sessions: `gpurun -- 'bash tools/_call.sh'` runs whatever the session last wrote here
+python -m pytest tests -m gpu -q -x 2>&1 | tail -2
+python bench.py --steps 10 --warmup 3 --skip-cpu --skip-torch > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -2 gpurun_out/bench.err
